@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py -- MC sample-weeks/s of the Monte Carlo hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # CPU arm (oracle port, host cores)
+
+A "step" is one whole job of the hot path: parameter draw, daily stepper over every sample,
+fold, quantile bands and means on the host (what run_model returns).  Workload at N=1 is
+BASELINE.json configs[1]: README USA scenario, 1e6 samples, N=50000, 564 days; under
+torchrun every rank folds 1e6 samples of a global range of N*1e6 (weak scaling) and the
+integer accumulators are merged with one NCCL all-reduce per pass.
+
+value   whole-job throughput from CUDA events on the library's stream (inputs -- 12 bounds --
+        resident; nothing else is read), max over ranks.
+e2e     the same job through the public Python API run_model() with host arguments and host
+        result arrays, wall clock around the call, per-step.
+One sample-week = 7 day-steps of model.py:82-127 for one sample.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+PKG = "covid19-vaccination-model_b200"
+USA = dict(pro=[35, 45], anti=[12, 25], pressure=[0.0, 0.02], tau=[5, 7], nv0=[1, 1.2], nvmax=[5, 10])
+DATES = dict(start_date="2020-12-15", end_date="2022-07-1")
+T_DAYS = 564
+N_POP = 50000
+CI_PCT = 95
+BYTES_PER_SAMPLE_WEEK = 112.0   # 4 int32 counts per sample-day if materialised
+HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def usa_bounds_frac():
+    import numpy as np
+
+    return np.concatenate([np.array(USA["pro"]) / 100, np.array(USA["anti"]) / 100,
+                           np.array(USA["pressure"], dtype=float), np.array(USA["tau"], dtype=float),
+                           np.array(USA["nv0"]) / 100, np.array(USA["nvmax"]) / 100])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag.is_set():
+                    break
+        except Exception:
+            pass
+
+    def finish(self) -> dict:
+        self.stop_flag.set()
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n_, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n_)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def cpu_port_rate(n_samples: int, threads: int, seed: int = 1):
+    """sample-weeks/s of the oracle port (C restatement of model.py:29-136 with numpy's own
+    MT19937 + Poisson algorithms) on `threads` host threads, incl. the per-date reduction."""
+    import numpy as np
+
+    import ref_oracle as ro
+
+    mt = ro.MT(seed)
+    b = usa_bounds_frac()
+    params, _ = ro.sample_param_combinations(mt, b[0:2], b[2:4], b[4:6], b[6:8], b[8:10], b[10:12],
+                                             n_samples)
+    ro.bulk_counts(seed, params[:256], T_DAYS, N_POP, threads=threads)      # warm caches / build
+    t0 = time.perf_counter()
+    daily, weekly = ro.bulk_counts(seed, params, T_DAYS, N_POP, threads=threads)
+    for arr in (daily[0], daily[1], daily[2], weekly):                      # model.py:220-223
+        np.quantile(arr, [0.025, 0.975], axis=1)
+        arr.mean(axis=1)
+    dt = time.perf_counter() - t0
+    return n_samples * T_DAYS / 7.0 / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n = args.cpu_samples
+    rates, times = [], []
+    for i in range(args.warmup + args.steps):
+        r, dt = cpu_port_rate(n, threads, seed=100 + i)
+        if i >= args.warmup:
+            rates.append(r); times.append(dt)
+    value = n * T_DAYS / 7.0 * len(times) / sum(times)
+    sample = (f"{n} samples x {T_DAYS} days per step (USA scenario), C port of model.py with "
+              f"numpy-identical MT19937/Poisson, {threads} pthreads, np.quantile+mean per date")
+    line = {
+        "impl": "reference", "metric": "MC sample-weeks/sec", "value": value, "unit": "sample-weeks/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
+        "config": {"workload": "README USA scenario (configs[1] bounds), bounded CPU sample",
+                   "samples_per_step": n, "days": T_DAYS, "N": N_POP, "CI": CI_PCT},
+        "cpu_baseline": {"value": value, "unit": "sample-weeks/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "sample-weeks/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": ("the reference is pure Python and cannot travel to the GPU box (no /root/reference "
+                 "there); this arm times the C restatement of its algorithm, which is ~15x faster "
+                 "per core than the Python original (SURVEY.md 6: 3.5-4.0e4 sample-weeks/s/core)"),
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--samples", type=int, default=1_000_000, help="samples per GPU per step")
+    ap.add_argument("--cpu-samples", type=int, default=200_000, help="samples of the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the native path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    vax = importlib.import_module(PKG)
+    nat = vax._native
+    dmod = vax.distributed
+    ctx = vax.default_context(local_rank)
+
+    n_global = args.samples * world
+    bounds = usa_bounds_frac()
+    q_lo, q_hi = (1 - CI_PCT / 100) / 2.0, (1 + CI_PCT / 100) / 2.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def all_reduce(t):
+        torch.cuda.current_stream(t.device).synchronize()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream(t.device).synchronize()
+
+    def one_job(seed):
+        cfg = nat.make_config(bounds, N_POP, T_DAYS, n_global, seed, q_lo, q_hi)
+        if world == 1:
+            return ctx.run_bounds(cfg)
+        return dmod.run_sharded(dmod.ContextEngine(ctx), cfg, rank, world, all_reduce,
+                                lambda: nat.ResultBuffers(T_DAYS))
+
+    # ---------------- device-timed leg ("value")
+    for i in range(args.warmup):
+        one_job(1000 + i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.15)
+    barrier()
+    launches0 = ctx.launch_count
+    dev_ms, fold_ms, pilot_ms, fold_launches, passes = [], [], [], 0, []
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()                       # L2 flush between timed iterations (outside the events)
+        torch.cuda.synchronize()
+        out = one_job(2000 + i)
+        dev_ms.append(out.c.device_ms); fold_ms.append(out.c.fold_ms); pilot_ms.append(out.c.pilot_ms)
+        fold_launches += out.c.fold_launches; passes.append(out.c.n_passes)
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    launches = ctx.launch_count - launches0
+    clocks = sampler.finish()
+
+    tot_ms = torch.tensor([sum(dev_ms)], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(tot_ms.item())
+    sample_weeks_per_step = n_global * T_DAYS / 7.0
+    value = sample_weeks_per_step * args.steps / (total_ms * 1e-3)
+
+    # ---------------- end-to-end leg through run_model (host args in, host arrays out)
+    e2e = None
+    if not args.no_e2e:
+        e2e_s = []
+        for i in range(min(args.warmup, 2) + args.steps):
+            flush.zero_(); torch.cuda.synchronize()
+            if dist is not None:
+                dist.barrier()
+            t0 = time.perf_counter()
+            res, err, msg = vax.run_model(USA["pro"], USA["anti"], USA["pressure"], USA["tau"], USA["nv0"],
+                                          USA["nvmax"], CI_PCT, n_global, N_POP, DATES, seed=3000 + i)
+            checksum = float(res["people_vaccinated_per_hundred"]["mean"][-1])  # host read of the result
+            dt = time.perf_counter() - t0
+            assert err == "" and checksum > 0
+            if i >= min(args.warmup, 2):
+                e2e_s.append(dt)
+        tt = torch.tensor([sum(e2e_s)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        W = nat.weeks(T_DAYS)
+        e2e = {"value": sample_weeks_per_step * len(e2e_s) / float(tt.item()), "unit": "sample-weeks/s",
+               "h2d_bytes_per_step": 12 * 8 + 64,                     # the bounds + scalars of vx_config
+               "d2h_bytes_per_step": 3 * (3 * T_DAYS + W) * 8 + 64,   # mean/lower/upper of 4 series
+               "ms_per_step": 1e3 * float(tt.item()) / len(e2e_s),
+               "api": "run_model(...) of covid19-vaccination-model_b200 (ctypes -> C ABI)"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel (the streaming-fold stepper)
+    peak, peak_src = measured_hbm_peak()
+    fold_ms_avg = sum(fold_ms) / max(fold_launches, 1)       # per launch, rank 0, CUDA events
+    units_per_launch = args.samples * T_DAYS / 7.0 * (sum(passes) / max(fold_launches, 1) if fold_launches else 1)
+    units_per_launch = args.samples * T_DAYS / 7.0
+    achieved = BYTES_PER_SAMPLE_WEEK * units_per_launch / (fold_ms_avg * 1e-3) / 1e9 if fold_launches else None
+    roofline = {
+        "kernel": "vx_sim_kernel<SIM_FOLD>", "bound": "hbm",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "ms_per_launch": fold_ms_avg, "share_of_step": sum(fold_ms) / sum(dev_ms) if sum(dev_ms) else None,
+        "note": ("algorithmic bytes = 112 B per sample-week (the int32 trajectories of SURVEY.md 8d) x "
+                 "sample-weeks per launch; the kernel folds them on the fly instead of writing them, so "
+                 "its real bound is instruction issue (see issue_roofline and DESIGN.md), and dram traffic "
+                 "is ~0 by design"),
+    }
+    sd_per_s = args.samples * T_DAYS / (fold_ms_avg * 1e-3) if fold_launches else None
+    issue = {"sample_days_per_s_per_gpu": sd_per_s,
+             "note": "issue-slot utilisation of the stepper is read from profiles/ (ncu sm__inst_executed)"}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, dt = cpu_port_rate(args.cpu_samples, threads)
+        cpu = {"value": rate, "unit": "sample-weeks/s", "cores": threads, "kind": "port",
+               "sample": f"{args.cpu_samples} samples x {T_DAYS} days of the same USA workload "
+                         f"({dt:.1f} s), C port of model.py, {threads} pthreads"}
+
+    line = {
+        "metric": "MC sample-weeks/sec", "value": value, "unit": "sample-weeks/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32 state / fp32 sampler / fp64 arrivals", "data": "synthetic",
+        "config": {"workload": "README USA scenario at 1e6 samples per GPU (BASELINE configs[1]); "
+                               "global range = n_gpus x samples_per_gpu, sharded by sample id",
+                   "samples_per_gpu": args.samples, "samples_global": n_global, "days": T_DAYS,
+                   "N": N_POP, "CI": CI_PCT, "seed": "2000+step", "l2": "flushed between steps (256 MiB memset)",
+                   "passes_per_step": statistics.mean(passes) if passes else 0},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu,
+        "wall_s_timed_region": wall_s,
+        "breakdown_ms_per_step": {"pilot": sum(pilot_ms) / args.steps, "fold": sum(fold_ms) / args.steps,
+                                  "total_device": sum(dev_ms) / args.steps},
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

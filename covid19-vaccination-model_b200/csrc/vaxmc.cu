@@ -1,0 +1,1081 @@
+// vaxmc.cu -- host side of libvaxmc.so: the C ABI declared in include/vaxmc.h.
+//
+// Orchestrates the reference's run_sampling (model.py:139-228) on one GPU (or one shard of
+// the sample range per GPU):
+//
+//   direct job   (n <= direct_max): stepper<DUMP> -> raw int32 rows [R][n] in HBM ->
+//                exact radix select per row (order statistics + sums).
+//   streamed job (n  > direct_max): the same on a PILOT (first n_p global samples) to place
+//                two narrow integer windows per date around the wanted ranks, then
+//                stepper<FOLD> over the whole shard accumulating, per date, an int64 sum,
+//                the count below each window and a unit-resolution histogram inside it.
+//                The slab is all-integer, so ranks merge it with one NCCL all-reduce(sum)
+//                and the order statistics read from it are EXACT and independent of the
+//                GPU count.  If a wanted rank falls outside its window (or the window had
+//                to be coarsened) vx_job_finalize narrows the windows and asks for another
+//                pass (VX_REFINE); the loop always terminates with the exact answer.
+//
+// There is no CPU fallback: every compute entry point fails with VX_ERR_NODEVICE when no
+// CUDA device is usable.
+#include "../../include/vaxmc.h"
+#include "vaxmc_kernels.cuh"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace vx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Target {
+    int64_t rank = 0;
+    int64_t lo = 0, hi = 0; // the order statistic is known to lie in [lo, hi]
+    bool resolved = false;
+    int64_t value = 0;
+};
+
+struct WinPlan { // host mirror of one device window + which targets it serves
+    Win w{0, 0, 0, 0};
+    int tgt[2] = {-1, -1};
+};
+
+struct Job {
+    vx_config cfg{};
+    int64_t shard_first = 0, shard_count = 0;
+    int T = 0, W = 0;
+    int64_t R = 0;
+    bool explicit_params = false;
+    bool direct = false;
+    bool stats_set = false, piloted = false, aborted = false, finished = false;
+    double gstats[4] = {0, 0, 0, 0};
+    int64_t n_pilot = 0;
+    int64_t vmax[4] = {0, 0, 0, 0};       // per raw-row class: n_vacc, dose, received, stock
+    // device buffers
+    double *d_params = nullptr;           // explicit tuples [n][6]
+    int32_t *d_dump = nullptr;
+    double *d_exp = nullptr;
+    Win *d_wins = nullptr;
+    unsigned long long *d_acc = nullptr;
+    int64_t acc_words = 0, acc_cap = 0;
+    long long *d_tgt = nullptr, *d_res = nullptr;
+    // host state of the streaming job
+    std::vector<Target> targets;          // [R][4]: lo_j, lo_j+1, hi_j, hi_j+1
+    std::vector<WinPlan> plan;            // [R][2]
+    std::vector<int64_t> pilot_stats;     // [R][4] pilot order statistics a_lo,b_lo,a_hi,b_hi
+    bool ranks_set = false;
+    int64_t n_total = 0;                  // samples folded (all ranks) = number_finished_samples
+    int64_t shard_done = 0;               // samples of this shard folded in pass 1
+    int n_passes = 0;
+    // results (host)
+    std::vector<double> mean[4], lower[4], upper[4];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
+    double fold_ms = 0.0, pilot_ms = 0.0;
+    int64_t fold_launches = 0;
+    std::chrono::steady_clock::time_point t_begin;
+};
+
+} // namespace
+
+struct vx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    Job *job = nullptr;
+    // options
+    int64_t max_bins = 65536;
+    int64_t chunk_samples = 1 << 20;
+    double pilot_sigmas = 6.0;
+    int64_t use_pilot = 1;
+    int sm_count = 148;
+};
+
+namespace {
+
+int fail(vx_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? VX_ERR_NOMEM : VX_ERR_CUDA,       \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__,        \
+                        __LINE__);                                                               \
+    } while (0)
+
+#define CKL()                                                                                    \
+    do {                                                                                         \
+        ctx->launches++;                                                                         \
+        CK(cudaGetLastError());                                                                  \
+    } while (0)
+
+void free_job(vx_ctx *ctx)
+{
+    Job *j = ctx->job;
+    if (!j) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(j->d_params); cudaFree(j->d_dump); cudaFree(j->d_exp); cudaFree(j->d_wins);
+    cudaFree(j->d_acc); cudaFree(j->d_tgt); cudaFree(j->d_res);
+    if (j->ev0) cudaEventDestroy(j->ev0);
+    if (j->ev1) cudaEventDestroy(j->ev1);
+    if (j->evA) cudaEventDestroy(j->evA);
+    if (j->evB) cudaEventDestroy(j->evB);
+    delete j;
+    ctx->job = nullptr;
+}
+
+int validate(vx_ctx *ctx, const vx_config *cfg, bool explicit_params, const double *params)
+{
+    if (!cfg) return fail(ctx, VX_ERR_ARG, "cfg is NULL");
+    if (cfg->T < 1 || cfg->T > 100000) return fail(ctx, VX_ERR_ARG, "T=%d out of range", cfg->T);
+    if (cfg->N < 1 || cfg->N > (int64_t)1 << 26) return fail(ctx, VX_ERR_ARG, "N out of range [1, 2^26]");
+    if (cfg->n_samples < 1) return fail(ctx, VX_ERR_ARG, "n_samples must be >= 1");
+    if (cfg->mode != VX_MODE_STOCHASTIC && cfg->mode != VX_MODE_EXPECTED)
+        return fail(ctx, VX_ERR_ARG, "unknown mode %d", cfg->mode);
+    if (!(cfg->q_lo >= 0.0 && cfg->q_lo <= 1.0 && cfg->q_hi >= 0.0 && cfg->q_hi <= 1.0))
+        return fail(ctx, VX_ERR_ARG, "quantile fractions must lie in [0,1]");
+    double nvmax_hi = 0.0;
+    if (!explicit_params) {
+        const double *b = cfg->bounds;
+        for (int i = 0; i < 12; ++i)
+            if (!std::isfinite(b[i])) return fail(ctx, VX_ERR_ARG, "non-finite bound");
+        if (std::min(b[4], b[5]) < 0.0)
+            return fail(ctx, VX_ERR_ARG, "lam < 0: negative pressure bound (numpy raises ValueError, model.py:116)");
+        if (std::min(b[6], b[7]) <= 0.0) return fail(ctx, VX_ERR_ARG, "tau bounds must be > 0");
+        if (std::min(b[0], b[1]) < 0.0 || std::min(b[2], b[3]) < 0.0 || std::min(b[8], b[9]) < 0.0 ||
+            std::min(b[10], b[11]) < 0.0)
+            return fail(ctx, VX_ERR_ARG, "negative fraction bound");
+        nvmax_hi = std::max(b[10], b[11]);
+    } else {
+        if (!params) return fail(ctx, VX_ERR_ARG, "params is NULL");
+        for (int64_t i = 0; i < cfg->n_samples; ++i) {
+            const double *p = params + 6 * i;
+            for (int k = 0; k < 6; ++k)
+                if (!std::isfinite(p[k])) return fail(ctx, VX_ERR_ARG, "non-finite parameter in tuple %lld", (long long)i);
+            if (p[0] + p[1] > 1.0) return fail(ctx, VX_ERR_ARG, "assert p_pro + p_anti <= 1.0 (model.py:63), tuple %lld", (long long)i);
+            if (p[0] < 0 || p[1] < 0 || p[2] < 0 || p[3] <= 0 || p[4] < 0 || p[5] < 0)
+                return fail(ctx, VX_ERR_ARG, "parameter out of range in tuple %lld", (long long)i);
+            nvmax_hi = std::max(nvmax_hi, p[5]);
+        }
+    }
+    const double Wd = (double)((cfg->T + 6) / 7);
+    if (Wd * (std::floor(nvmax_hi * (double)cfg->N) + 1.0) >= 134217728.0)
+        return fail(ctx, VX_ERR_ARG, "cumulative deliveries may exceed 2^27 doses: unsupported size");
+    return VX_OK;
+}
+
+inline int series_of_row(const Job *j, int64_t row)
+{
+    if (row < j->T) return 0;
+    if (row < j->T + j->W) return 1;
+    if (row < j->T + 2 * j->W) return 2;
+    return 3;
+}
+
+int alloc_results(Job *j)
+{
+    const int len[4] = {j->T, j->W, j->T, j->T};
+    for (int s = 0; s < 4; ++s) {
+        j->mean[s].assign(len[s], 0.0);
+        j->lower[s].assign(len[s], 0.0);
+        j->upper[s].assign(len[s], 0.0);
+    }
+    return 0;
+}
+
+// (series, date index) -> raw row
+inline int64_t row_of(const Job *j, int s, int i)
+{
+    switch (s) {
+    case 0: return i;
+    case 1: return j->T + i;
+    case 2: return j->T + j->W + i / 7;
+    default: return j->T + 2 * (int64_t)j->W + i;
+    }
+}
+
+void fill_from_counts(Job *j, const std::vector<int64_t> &ord /*[R][4]*/,
+                      const std::vector<long long> &sums, int64_t n)
+{
+    int64_t p0, n0, p1, n1;
+    double g0, g1;
+    vx_host_quantile_index(n, j->cfg.q_lo, &p0, &n0, &g0);
+    vx_host_quantile_index(n, j->cfg.q_hi, &p1, &n1, &g1);
+    const int len[4] = {j->T, j->W, j->T, j->T};
+    for (int s = 0; s < 4; ++s)
+        for (int i = 0; i < len[s]; ++i) {
+            const int64_t r = row_of(j, s, i);
+            const int64_t *o = &ord[r * 4];
+            j->lower[s][i] = vx_host_lerp(vx_host_count_to_value(s, o[0], j->cfg.N),
+                                          vx_host_count_to_value(s, o[1], j->cfg.N), g0);
+            j->upper[s][i] = vx_host_lerp(vx_host_count_to_value(s, o[2], j->cfg.N),
+                                          vx_host_count_to_value(s, o[3], j->cfg.N), g1);
+            j->mean[s][i] = vx_host_count_to_value(s, sums[r], j->cfg.N) / (double)n;
+        }
+}
+
+int copy_results(vx_ctx *ctx, vx_result *res)
+{
+    Job *j = ctx->job;
+    const int len[4] = {j->T, j->W, j->T, j->T};
+    for (int s = 0; s < 4; ++s) {
+        if (res->mean[s]) memcpy(res->mean[s], j->mean[s].data(), sizeof(double) * len[s]);
+        if (res->lower[s]) memcpy(res->lower[s], j->lower[s].data(), sizeof(double) * len[s]);
+        if (res->upper[s]) memcpy(res->upper[s], j->upper[s].data(), sizeof(double) * len[s]);
+    }
+    return VX_OK;
+}
+
+void fill_result_scalars(vx_ctx *ctx, vx_result *res)
+{
+    Job *j = ctx->job;
+    res->n_finished = j->n_total;
+    res->aborted = j->aborted ? 1 : 0;
+    res->n_passes = j->n_passes;
+    res->n_rejected = (int64_t)j->gstats[0];
+    const double n = j->gstats[3];
+    if (n > 0) {
+        const double m = j->gstats[1] / n;
+        const double var = std::max(j->gstats[2] / n - m * m, 0.0);
+        res->soft_no_mean = m;
+        res->soft_no_std = std::sqrt(var);
+    } else {
+        res->soft_no_mean = res->soft_no_std = 0.0;
+    }
+}
+
+SimArgs make_args(const Job *j, int64_t first, int64_t count, const double *d_params)
+{
+    SimArgs a{};
+    memcpy(a.bd.b, j->cfg.bounds, sizeof a.bd.b);
+    a.params = d_params;
+    a.seed = j->cfg.seed;
+    a.first = first;
+    a.count = count;
+    a.N = j->cfg.N;
+    a.T = j->T;
+    a.W = j->W;
+    return a;
+}
+
+int upload_rcp(vx_ctx *ctx)
+{
+    float h[72];
+    h[0] = 0.f;
+    for (int k = 1; k < 72; ++k) h[k] = 1.0f / (float)k;
+    CK(cudaMemcpyToSymbol(c_rcp, h, sizeof h));
+    return VX_OK;
+}
+
+// ---- window planning ---------------------------------------------------------------
+inline uint32_t shift_for(int64_t width, int64_t max_bins)
+{
+    uint32_t s = 0;
+    while (((width + ((int64_t)1 << s) - 1) >> s) > max_bins) ++s;
+    return s;
+}
+
+// Build the device windows of the next pass from the unresolved targets.
+int plan_windows(vx_ctx *ctx, bool from_pilot)
+{
+    Job *j = ctx->job;
+    const int64_t R = j->R;
+    j->plan.assign(R * 2, WinPlan());
+    uint64_t off = 0;
+    for (int64_t r = 0; r < R; ++r) {
+        Target *t = &j->targets[r * 4];
+        int nw = 0;
+        if (from_pilot) {
+            const int64_t *ps = &j->pilot_stats[r * 4];
+            for (int q = 0; q < 2; ++q) {
+                int64_t a = ps[2 * q], b = ps[2 * q + 1];
+                a = std::max(a, t[2 * q].lo);
+                b = std::min(std::max(b, a), t[2 * q].hi);
+                WinPlan &wp = j->plan[r * 2 + q];
+                const int64_t width = b - a + 1;
+                const uint32_t sh = shift_for(width, ctx->max_bins);
+                const int64_t nb = (width + ((int64_t)1 << sh) - 1) >> sh;
+                wp.w.a = (int)a; wp.w.shift = sh; wp.w.len = (uint32_t)(nb << sh);
+                wp.tgt[0] = 2 * q; wp.tgt[1] = 2 * q + 1;
+            }
+            nw = 2;
+        } else {
+            bool used[4] = {false, false, false, false};
+            for (int k = 0; k < 4 && nw < 2; ++k) {
+                if (t[k].resolved || used[k]) continue;
+                WinPlan &wp = j->plan[r * 2 + nw];
+                int64_t lo = t[k].lo, hi = t[k].hi;
+                wp.tgt[0] = k; used[k] = true;
+                for (int m = k + 1; m < 4; ++m) {
+                    if (t[m].resolved || used[m]) continue;
+                    const int64_t ulo = std::min(lo, t[m].lo), uhi = std::max(hi, t[m].hi);
+                    if (uhi - ulo + 1 <= (hi - lo + 1) + (t[m].hi - t[m].lo + 1) + 1) {
+                        wp.tgt[1] = m; used[m] = true; lo = ulo; hi = uhi;
+                    }
+                    break; // at most two targets per window, neighbours only
+                }
+                const int64_t width = hi - lo + 1;
+                const uint32_t sh = shift_for(width, ctx->max_bins);
+                const int64_t nb = (width + ((int64_t)1 << sh) - 1) >> sh;
+                wp.w.a = (int)lo; wp.w.shift = sh; wp.w.len = (uint32_t)(nb << sh);
+                ++nw;
+            }
+        }
+        for (int q = 0; q < 2; ++q) {
+            WinPlan &wp = j->plan[r * 2 + q];
+            if (off + (wp.w.len >> wp.w.shift) > 0xfffffff0ull)
+                return fail(ctx, VX_ERR_NOMEM, "window histograms exceed 2^32 bins");
+            wp.w.off = (uint32_t)off;
+            off += wp.w.len >> wp.w.shift;
+        }
+    }
+    const int64_t words = ACC_HDR + 3 * R + (int64_t)off;
+    if (words > j->acc_cap) {
+        if (j->d_acc) CK(cudaFree(j->d_acc));
+        j->d_acc = nullptr;
+        CK(cudaMalloc(&j->d_acc, sizeof(unsigned long long) * words));
+        j->acc_cap = words;
+    }
+    j->acc_words = words;
+    std::vector<Win> hw(R * 2);
+    for (int64_t i = 0; i < R * 2; ++i) hw[i] = j->plan[i].w;
+    if (!j->d_wins) CK(cudaMalloc(&j->d_wins, sizeof(Win) * R * 2));
+    if (!j->d_tgt) CK(cudaMalloc(&j->d_tgt, sizeof(long long) * R * 4));
+    if (!j->d_res) CK(cudaMalloc(&j->d_res, sizeof(long long) * R * 4));
+    CK(cudaMemcpyAsync(j->d_wins, hw.data(), sizeof(Win) * R * 2, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
+}
+
+int run_select_i32(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, int64_t n,
+                   const std::vector<int64_t> &ranks, std::vector<int64_t> &ord,
+                   std::vector<long long> &sums)
+{
+    const int K = (int)ranks.size();
+    int64_t *d_ranks = nullptr;
+    int32_t *d_out = nullptr;
+    long long *d_sums = nullptr;
+    CK(cudaMalloc(&d_ranks, sizeof(int64_t) * K));
+    CK(cudaMalloc(&d_out, sizeof(int32_t) * rows * K));
+    CK(cudaMalloc(&d_sums, sizeof(long long) * rows));
+    CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, ctx->stream));
+    vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
+    CKL();
+    std::vector<int32_t> ho(rows * K);
+    sums.resize(rows);
+    CK(cudaMemcpyAsync(ho.data(), d_out, sizeof(int32_t) * rows * K, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(sums.data(), d_sums, sizeof(long long) * rows, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ord.resize(rows * K);
+    for (int64_t i = 0; i < rows * K; ++i) ord[i] = ho[i];
+    cudaFree(d_ranks); cudaFree(d_out); cudaFree(d_sums);
+    return VX_OK;
+}
+
+int need_device(vx_ctx *ctx)
+{
+    if (!ctx) return VX_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return VX_OK;
+}
+
+int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double *d_params,
+                int32_t *d_dump, int64_t ld)
+{
+    SimArgs a = make_args(j, first, count, d_params);
+    a.dump = d_dump;
+    a.dump_stride = ld;
+    const int64_t grid = (count + SIM_THREADS - 1) / SIM_THREADS;
+    vx_sim_kernel<SIM_DUMP><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+    CKL();
+    return VX_OK;
+}
+
+int64_t default_pilot(int64_t n)
+{
+    int64_t p = 65536;
+    while (p < n / 16 && p < ((int64_t)1 << 20)) p <<= 1;
+    return p;
+}
+
+// ---- the expected-value job (always direct) ----------------------------------------
+int run_expected(vx_ctx *ctx)
+{
+    Job *j = ctx->job;
+    const int64_t n = j->cfg.n_samples;
+    const int64_t RE = 4 * (int64_t)j->T + j->W;
+    if ((double)RE * (double)n * 8.0 > 64e9)
+        return fail(ctx, VX_ERR_ARG, "expected-value mode materialises fp64 trajectories: n_samples too large");
+    CK(cudaMalloc(&j->d_exp, sizeof(double) * RE * n));
+    SimArgs a = make_args(j, 0, n, j->d_params);
+    vx_expected_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, j->d_exp, n);
+    CKL();
+    int64_t p0, n0, p1, n1; double g0, g1;
+    vx_host_quantile_index(n, j->cfg.q_lo, &p0, &n0, &g0);
+    vx_host_quantile_index(n, j->cfg.q_hi, &p1, &n1, &g1);
+    const int64_t hr[4] = {p0, n0, p1, n1};
+    int64_t *d_ranks = nullptr; double *d_out = nullptr, *d_sums = nullptr;
+    CK(cudaMalloc(&d_ranks, sizeof hr));
+    CK(cudaMalloc(&d_out, sizeof(double) * RE * 4));
+    CK(cudaMalloc(&d_sums, sizeof(double) * RE));
+    CK(cudaMemcpyAsync(d_ranks, hr, sizeof hr, cudaMemcpyHostToDevice, ctx->stream));
+    vx_select_kernel<double><<<(unsigned)RE, SEL_THREADS, 0, ctx->stream>>>(j->d_exp, n, n, d_ranks, 4, d_out, d_sums);
+    CKL();
+    std::vector<double> ho(RE * 4), hs(RE);
+    CK(cudaMemcpyAsync(ho.data(), d_out, sizeof(double) * RE * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hs.data(), d_sums, sizeof(double) * RE, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_ranks); cudaFree(d_out); cudaFree(d_sums);
+    alloc_results(j);
+    const int len[4] = {j->T, j->W, j->T, j->T};
+    for (int s = 0; s < 4; ++s)
+        for (int i = 0; i < len[s]; ++i) {
+            const int64_t r = (s == 1) ? 4 * (int64_t)j->T + i : (int64_t)s * j->T + i;
+            j->lower[s][i] = vx_host_lerp(ho[r * 4], ho[r * 4 + 1], g0);
+            j->upper[s][i] = vx_host_lerp(ho[r * 4 + 2], ho[r * 4 + 3], g1);
+            j->mean[s][i] = hs[r] / (double)n;
+        }
+    j->n_total = n;
+    j->finished = true;
+    return VX_OK;
+}
+
+} // namespace
+
+// =====================================================================================
+extern "C" {
+
+const char *vx_version(void) { return "vaxmc 0.1 (sm_100a)"; }
+
+int vx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int vx_create(vx_ctx **out, int device)
+{
+    vx_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, VX_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(nullptr, VX_ERR_NODEVICE, "no CUDA device: libvaxmc has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(nullptr, VX_ERR_ARG, "device %d not in [0,%d)", device, n);
+    vx_ctx *c = new vx_ctx();
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int sm = 0;
+        cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        if (sm > 0) c->sm_count = sm;
+        ctx = c;
+        if (upload_rcp(ctx) != VX_OK) { g_create_error = c->err; cudaStreamDestroy(c->stream); delete c; return VX_ERR_CUDA; }
+        *out = c;
+        return VX_OK;
+    }
+    delete c;
+    return fail(nullptr, VX_ERR_CUDA, "vx_create: %s", cudaGetErrorString(e));
+}
+
+void vx_destroy(vx_ctx *ctx)
+{
+    if (!ctx) return;
+    free_job(ctx);
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *vx_last_error(vx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int64_t vx_launch_count(vx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vx_set_option(vx_ctx *ctx, const char *name, double value)
+{
+    if (!ctx || !name) return VX_ERR_ARG;
+    const std::string s(name);
+    if (s == "max_bins") { if (value < 2 || value > (1 << 24)) return fail(ctx, VX_ERR_ARG, "max_bins out of range"); ctx->max_bins = (int64_t)value; }
+    else if (s == "chunk_samples") { if (value < 256) return fail(ctx, VX_ERR_ARG, "chunk_samples too small"); ctx->chunk_samples = (int64_t)value; }
+    else if (s == "pilot_sigmas") { if (!(value >= 0)) return fail(ctx, VX_ERR_ARG, "pilot_sigmas < 0"); ctx->pilot_sigmas = value; }
+    else if (s == "use_pilot") ctx->use_pilot = value != 0;
+    else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
+    return VX_OK;
+}
+
+// ---- host-only helpers -----------------------------------------------------------------
+double vx_host_lerp(double a, double b, double t)
+{
+    // numpy/lib/_function_base_impl.py:_lerp
+    const double diff = b - a;
+    double r = a + diff * t;
+    if (t >= 0.5) r = b - diff * (1 - t);
+    return r;
+}
+
+void vx_host_quantile_index(int64_t n, double q, int64_t *prev, int64_t *next, double *gamma)
+{
+    // method="linear": virtual index (n-1)*q; _get_indexes + _get_gamma
+    const double vi = (double)(n - 1) * q;
+    double p = std::floor(vi);
+    int64_t pi = (int64_t)p, ni = pi + 1;
+    if (vi >= (double)(n - 1)) { pi = n - 1; ni = n - 1; }
+    if (vi < 0) { pi = 0; ni = 0; }
+    *prev = pi; *next = ni;
+    *gamma = vi - p;
+}
+
+double vx_host_count_to_value(int series, int64_t count, int64_t N)
+{
+    const double c = (double)count, Nd = (double)N;
+    switch (series) {
+    case 0: return (c / Nd) * 100;   // fract_pop_vaccinated * 100          model.py:112,124
+    case 1: return c * 1e6 / Nd;     // delta_n_vacc * 1e6 / N              model.py:125
+    default: return c * 100 / Nd;    // cum received / stock * 100 / N      model.py:126-127
+    }
+}
+
+int32_t vx_host_weeks(int32_t T) { return (T + 6) / 7; }
+int64_t vx_host_rows(int32_t T) { return 2 * (int64_t)T + 2 * (int64_t)((T + 6) / 7); }
+
+// ---- staged job --------------------------------------------------------------------------
+static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_first,
+                            int64_t shard_count, const double *h_params)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    free_job(ctx);
+    rc = validate(ctx, cfg, h_params != nullptr, h_params);
+    if (rc) return rc;
+    if (shard_first < 0 || shard_count < 0 || shard_first + shard_count > cfg->n_samples)
+        return fail(ctx, VX_ERR_ARG, "shard [%lld,+%lld) outside [0,%lld)", (long long)shard_first,
+                    (long long)shard_count, (long long)cfg->n_samples);
+    Job *j = new Job();
+    ctx->job = j;
+    j->cfg = *cfg;
+    j->shard_first = shard_first;
+    j->shard_count = shard_count;
+    j->T = cfg->T;
+    j->W = (cfg->T + 6) / 7;
+    j->R = 2 * (int64_t)j->T + 2 * (int64_t)j->W;
+    j->explicit_params = h_params != nullptr;
+    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 131072;
+    j->direct = (cfg->mode == VX_MODE_EXPECTED) || cfg->n_samples <= dmax;
+    j->t_begin = std::chrono::steady_clock::now();
+    double nvmax_hi = std::max(cfg->bounds[10], cfg->bounds[11]);
+    if (h_params) {
+        nvmax_hi = 0;
+        for (int64_t i = 0; i < cfg->n_samples; ++i) nvmax_hi = std::max(nvmax_hi, h_params[6 * i + 5]);
+        CK(cudaMalloc(&j->d_params, sizeof(double) * 6 * cfg->n_samples));
+        CK(cudaMemcpyAsync(j->d_params, h_params, sizeof(double) * 6 * cfg->n_samples, cudaMemcpyHostToDevice, ctx->stream));
+        j->gstats[3] = (double)cfg->n_samples;
+        j->stats_set = true;
+    }
+    const int64_t recv_max = (int64_t)j->W * ((int64_t)std::floor(nvmax_hi * (double)cfg->N) + 1);
+    j->vmax[0] = cfg->N; j->vmax[1] = 2 * cfg->N; j->vmax[2] = recv_max; j->vmax[3] = recv_max;
+    CK(cudaEventCreate(&j->ev0));
+    CK(cudaEventCreate(&j->ev1));
+    CK(cudaEventCreate(&j->evA));
+    CK(cudaEventCreate(&j->evB));
+    CK(cudaEventRecord(j->ev0, ctx->stream));
+    return VX_OK;
+}
+
+int vx_job_begin(vx_ctx *ctx, const vx_config *cfg, int64_t shard_first, int64_t shard_count)
+{
+    return job_begin_common(ctx, cfg, shard_first, shard_count, nullptr);
+}
+
+int vx_job_param_stats(vx_ctx *ctx, double stats[4])
+{
+    if (!ctx || !ctx->job || !stats) return fail(ctx, VX_ERR_STATE, "no job");
+    Job *j = ctx->job;
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    stats[0] = stats[1] = stats[2] = 0.0;
+    stats[3] = (double)j->shard_count;
+    if (j->explicit_params || j->shard_count == 0) return VX_OK;
+    const double *b = j->cfg.bounds;
+    if (std::min(b[0], b[1]) + std::min(b[2], b[3]) > 1.0) {
+        // no acceptable pair exists: the reference burns 10*n_rep+1 rejections and aborts
+        stats[0] = 10.0 * (double)j->cfg.n_samples + 1.0;
+        return VX_OK;
+    }
+    const int64_t n = j->shard_count, grid = (n + 255) / 256;
+    unsigned long long *d_stop = nullptr;
+    double *d_part = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_stop, 16));
+    CK(cudaMalloc(&d_part, sizeof(double) * 3 * grid));
+    CK(cudaMalloc(&d_out, sizeof(double) * 3));
+    const unsigned long long hstop[2] = {0ull, (unsigned long long)(10 * j->cfg.n_samples)};
+    CK(cudaMemcpyAsync(d_stop, hstop, 16, cudaMemcpyHostToDevice, ctx->stream));
+    Bounds bd;
+    memcpy(bd.b, b, sizeof bd.b);
+    vx_param_stats_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(bd, j->cfg.seed, j->shard_first, n, d_stop, d_part);
+    CKL();
+    vx_reduce_stats_kernel<<<1, 1024, 0, ctx->stream>>>(d_part, grid, d_out);
+    CKL();
+    CK(cudaMemcpyAsync(stats, d_out, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_stop); cudaFree(d_part); cudaFree(d_out);
+    return VX_OK;
+}
+
+int vx_job_set_param_stats(vx_ctx *ctx, const double stats[4])
+{
+    if (!ctx || !ctx->job || !stats) return fail(ctx, VX_ERR_STATE, "no job");
+    Job *j = ctx->job;
+    memcpy(j->gstats, stats, sizeof j->gstats);
+    j->stats_set = true;
+    // model.py:282-287: abort when the rejection count exceeds 10 * n_rep
+    j->aborted = stats[0] > 10.0 * (double)j->cfg.n_samples;
+    return j->aborted ? 1 : 0;
+}
+
+int vx_job_is_direct(vx_ctx *ctx) { return (ctx && ctx->job && ctx->job->direct) ? 1 : 0; }
+
+int vx_job_pilot(vx_ctx *ctx)
+{
+    if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
+    Job *j = ctx->job;
+    if (!j->stats_set) return fail(ctx, VX_ERR_STATE, "vx_job_set_param_stats must precede vx_job_pilot");
+    if (j->aborted) return fail(ctx, VX_ERR_STATE, "job aborted by the rejection rule");
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    j->piloted = true;
+    struct PilotTimer {
+        vx_ctx *c; Job *j;
+        PilotTimer(vx_ctx *c_, Job *j_) : c(c_), j(j_) { cudaEventRecord(j->evA, c->stream); }
+        ~PilotTimer() {
+            cudaEventRecord(j->evB, c->stream);
+            cudaEventSynchronize(j->evB);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, j->evA, j->evB) == cudaSuccess) j->pilot_ms += ms;
+        }
+    } pilot_timer(ctx, j);
+    if (j->cfg.mode == VX_MODE_EXPECTED) return run_expected(ctx);
+
+    const int64_t n = j->cfg.n_samples, R = j->R;
+    alloc_results(j);
+    // certain bounds of every order statistic
+    j->targets.assign(R * 4, Target());
+    for (int64_t r = 0; r < R; ++r)
+        for (int k = 0; k < 4; ++k) { j->targets[r * 4 + k].lo = 0; j->targets[r * 4 + k].hi = j->vmax[series_of_row(j, r)]; }
+
+    if (!j->direct && !ctx->use_pilot) {
+        j->n_pilot = 0;
+        return plan_windows(ctx, false);
+    }
+    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(n));
+    j->n_pilot = np;
+    if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
+    CK(cudaMalloc(&j->d_dump, sizeof(int32_t) * R * np));
+    rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np);
+    if (rc) return rc;
+
+    std::vector<int64_t> ranks(4), ord;
+    std::vector<long long> sums;
+    if (j->direct) {
+        double g;
+        vx_host_quantile_index(n, j->cfg.q_lo, &ranks[0], &ranks[1], &g);
+        vx_host_quantile_index(n, j->cfg.q_hi, &ranks[2], &ranks[3], &g);
+        rc = run_select_i32(ctx, j->d_dump, R, np, np, ranks, ord, sums);
+        if (rc) return rc;
+        fill_from_counts(j, ord, sums, n);
+        j->n_total = n;
+        j->finished = true;
+        return VX_OK;
+    }
+    // pilot order statistics bracketing each wanted quantile by +-k sigma of its rank
+    const double qs[2] = {j->cfg.q_lo, j->cfg.q_hi};
+    for (int q = 0; q < 2; ++q) {
+        const double sd = std::sqrt(std::max(qs[q] * (1 - qs[q]), 0.0));
+        const double delta = ctx->pilot_sigmas * sd * (1.0 / std::sqrt((double)np) + 1.0 / std::sqrt((double)n)) + 2.0 / (double)np;
+        const double ra = std::floor((double)(np - 1) * (qs[q] - delta)) - 1.0;
+        const double rb = std::ceil((double)(np - 1) * (qs[q] + delta)) + 1.0;
+        ranks[2 * q] = (int64_t)std::min(std::max(ra, 0.0), (double)(np - 1));
+        ranks[2 * q + 1] = (int64_t)std::min(std::max(rb, 0.0), (double)(np - 1));
+    }
+    rc = run_select_i32(ctx, j->d_dump, R, np, np, ranks, ord, sums);
+    if (rc) return rc;
+    j->pilot_stats = ord;
+    // a bracket that ran off either end of the pilot sample is open on that side
+    for (int64_t r = 0; r < R; ++r)
+        for (int q = 0; q < 2; ++q) {
+            if (ranks[2 * q] == 0) j->pilot_stats[r * 4 + 2 * q] = 0;
+            if (ranks[2 * q + 1] == np - 1) j->pilot_stats[r * 4 + 2 * q + 1] = j->vmax[series_of_row(j, r)];
+        }
+    CK(cudaFree(j->d_dump));
+    j->d_dump = nullptr;
+    return plan_windows(ctx, true);
+}
+
+int vx_job_acc(vx_ctx *ctx, void **device_ptr, int64_t *n_words)
+{
+    if (!ctx || !ctx->job || !device_ptr || !n_words) return fail(ctx, VX_ERR_STATE, "no job");
+    Job *j = ctx->job;
+    *device_ptr = j->direct ? nullptr : (void *)j->d_acc;
+    *n_words = j->direct ? 0 : j->acc_words;
+    return VX_OK;
+}
+
+int vx_job_accumulate(vx_ctx *ctx)
+{
+    if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
+    Job *j = ctx->job;
+    if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_accumulate");
+    if (j->direct || j->finished) return VX_OK;
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(j->d_acc, 0, sizeof(unsigned long long) * j->acc_words, ctx->stream));
+    const bool first_pass = j->n_passes == 0;
+    const int64_t todo = first_pass ? j->shard_count : j->shard_done;
+    const bool timed = first_pass && j->cfg.max_running_time > 0.0;
+    const int64_t chunk = timed ? ctx->chunk_samples : ((int64_t)1 << 30);
+    int64_t done = 0;
+    CK(cudaEventRecord(j->evA, ctx->stream));
+    while (done < todo) {
+        const int64_t cnt = std::min(chunk, todo - done);
+        SimArgs a = make_args(j, j->shard_first + done, cnt,
+                              j->d_params ? j->d_params + 6 * (j->shard_first + done) : nullptr);
+        a.wins = j->d_wins;
+        a.acc = j->d_acc;
+        const int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
+        vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+        CKL();
+        j->fold_launches++;
+        done += cnt;
+        if (timed) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - j->t_begin).count();
+            if (el > j->cfg.max_running_time) break;   // model.py:187-189
+        }
+    }
+    if (first_pass) j->shard_done = done;
+    j->n_passes++;
+    CK(cudaEventRecord(j->evB, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float fms = 0.f;
+    cudaEventElapsedTime(&fms, j->evA, j->evB);
+    j->fold_ms += fms;
+    return VX_OK;
+}
+
+int vx_job_finalize(vx_ctx *ctx, vx_result *res)
+{
+    if (!ctx || !ctx->job || !res) return fail(ctx, VX_ERR_STATE, "no job");
+    Job *j = ctx->job;
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_finalize");
+    if (!j->finished) {
+        const int64_t R = j->R;
+        unsigned long long hdr[ACC_HDR];
+        CK(cudaMemcpyAsync(hdr, j->d_acc, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const int64_t n = (int64_t)hdr[0];
+        if (n < 1) return fail(ctx, VX_ERR_STATE, "no samples were folded");
+        if (!j->ranks_set) {
+            j->n_total = n;
+            int64_t p0, n0, p1, n1; double g;
+            vx_host_quantile_index(n, j->cfg.q_lo, &p0, &n0, &g);
+            vx_host_quantile_index(n, j->cfg.q_hi, &p1, &n1, &g);
+            for (int64_t r = 0; r < R; ++r) {
+                Target *t = &j->targets[r * 4];
+                t[0].rank = p0; t[1].rank = n0; t[2].rank = p1; t[3].rank = n1;
+            }
+            j->ranks_set = true;
+        } else if (n != j->n_total) {
+            return fail(ctx, VX_ERR_STATE, "pass folded %lld samples, first pass folded %lld", (long long)n, (long long)j->n_total);
+        }
+        std::vector<long long> ht(R * 4);
+        for (int64_t i = 0; i < R * 2; ++i)
+            for (int k = 0; k < 2; ++k) {
+                const int ti = j->plan[i].tgt[k];
+                ht[i * 2 + k] = ti < 0 ? -1 : j->targets[(i / 2) * 4 + ti].rank;
+            }
+        CK(cudaMemcpyAsync(j->d_tgt, ht.data(), sizeof(long long) * R * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const int64_t warps = 2 * R, grid = (warps * 32 + 255) / 256;
+        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R);
+        CKL();
+        std::vector<long long> hres(R * 4);
+        std::vector<long long> sums(R);
+        CK(cudaMemcpyAsync(hres.data(), j->d_res, sizeof(long long) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(sums.data(), j->d_acc + ACC_HDR, sizeof(long long) * R, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool all = true;
+        for (int64_t i = 0; i < R * 2; ++i) {
+            const WinPlan &wp = j->plan[i];
+            for (int k = 0; k < 2; ++k) {
+                if (wp.tgt[k] < 0) continue;
+                Target &t = j->targets[(i / 2) * 4 + wp.tgt[k]];
+                const long long rr = hres[i * 2 + k];
+                const int status = (int)(rr >> 32);
+                const int64_t bin = (int64_t)(rr & 0xffffffffll);
+                const int64_t a = wp.w.a, len = wp.w.len;
+                if (status == 1) t.hi = std::min(t.hi, a - 1);
+                else if (status == 2) t.lo = std::max(t.lo, a + len);
+                else {
+                    t.lo = std::max(t.lo, a + (bin << wp.w.shift));
+                    t.hi = std::min(t.hi, a + ((bin + 1) << wp.w.shift) - 1);
+                }
+                if (t.lo > t.hi) return fail(ctx, VX_ERR_STATE, "window bookkeeping lost rank %lld of row %lld", (long long)t.rank, (long long)(i / 2));
+                if (t.lo == t.hi) { t.resolved = true; t.value = t.lo; }
+            }
+        }
+        for (const Target &t : j->targets) all = all && t.resolved;
+        if (!all) {
+            rc = plan_windows(ctx, false);
+            if (rc) return rc;
+            return VX_REFINE;
+        }
+        std::vector<int64_t> ord(R * 4);
+        for (int64_t i = 0; i < R * 4; ++i) ord[i] = j->targets[i].value;
+        fill_from_counts(j, ord, sums, n);
+        j->finished = true;
+    }
+    CK(cudaEventRecord(j->ev1, ctx->stream));
+    CK(cudaEventSynchronize(j->ev1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, j->ev0, j->ev1);
+    res->device_ms = ms;
+    res->fold_ms = j->fold_ms;
+    res->pilot_ms = j->pilot_ms;
+    res->fold_launches = j->fold_launches;
+    fill_result_scalars(ctx, res);
+    return copy_results(ctx, res);
+}
+
+int vx_job_end(vx_ctx *ctx)
+{
+    if (!ctx) return VX_ERR_ARG;
+    free_job(ctx);
+    return VX_OK;
+}
+
+// ---- whole jobs ------------------------------------------------------------------------
+static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
+{
+    Job *j = ctx->job;
+    int rc;
+    if (!j->explicit_params) {
+        double st[4];
+        rc = vx_job_param_stats(ctx, st);
+        if (rc) return rc;
+        if (vx_job_set_param_stats(ctx, st) == 1) {
+            res->device_ms = 0; res->fold_ms = 0; res->pilot_ms = 0; res->fold_launches = 0;
+            fill_result_scalars(ctx, res);
+            res->n_finished = 0;
+            return VX_OK;
+        }
+    }
+    rc = vx_job_pilot(ctx);
+    if (rc) return rc;
+    if (counts_out) {
+        if (!j->direct || !j->d_dump) return fail(ctx, VX_ERR_ARG, "counts_out needs a direct job (n_samples <= direct_max)");
+        CK(cudaMemcpyAsync(counts_out, j->d_dump, sizeof(int32_t) * j->R * j->cfg.n_samples, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (int it = 0; it < 64; ++it) {
+        rc = vx_job_accumulate(ctx);
+        if (rc) return rc;
+        rc = vx_job_finalize(ctx, res);
+        if (rc != VX_REFINE) return rc;
+    }
+    return fail(ctx, VX_ERR_STATE, "window refinement did not converge");
+}
+
+int vx_run_bounds(vx_ctx *ctx, const vx_config *cfg, vx_result *res)
+{
+    if (!ctx || !res) return VX_ERR_ARG;
+    int rc = job_begin_common(ctx, cfg, 0, cfg ? cfg->n_samples : 0, nullptr);
+    if (rc == VX_OK) rc = run_job(ctx, res, nullptr);
+    const std::string keep = ctx->err;
+    free_job(ctx);
+    ctx->err = keep;
+    return rc;
+}
+
+int vx_run_params(vx_ctx *ctx, const vx_config *cfg, const double *params, vx_result *res,
+                  int32_t *counts_out)
+{
+    if (!ctx || !res) return VX_ERR_ARG;
+    if (!params) return fail(ctx, VX_ERR_ARG, "params is NULL");
+    int rc = job_begin_common(ctx, cfg, 0, cfg ? cfg->n_samples : 0, params);
+    if (rc == VX_OK && counts_out && cfg->mode != VX_MODE_STOCHASTIC)
+        rc = fail(ctx, VX_ERR_ARG, "counts_out is only available in stochastic mode");
+    if (rc == VX_OK) rc = run_job(ctx, res, counts_out);
+    const std::string keep = ctx->err;
+    free_job(ctx);
+    ctx->err = keep;
+    return rc;
+}
+
+// ---- pieces ----------------------------------------------------------------------------
+int vx_sample_params(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t count,
+                     double *params_out, double *p_soft_no_out)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    rc = validate(ctx, cfg, false, nullptr);
+    if (rc) return rc;
+    if (count < 0 || !params_out) return fail(ctx, VX_ERR_ARG, "bad output");
+    if (count == 0) return VX_OK;
+    double *d_p = nullptr, *d_s = nullptr;
+    CK(cudaMalloc(&d_p, sizeof(double) * 6 * count));
+    if (p_soft_no_out) CK(cudaMalloc(&d_s, sizeof(double) * count));
+    Bounds bd;
+    memcpy(bd.b, cfg->bounds, sizeof bd.b);
+    vx_sample_params_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(bd, cfg->seed, first, count, d_p, d_s);
+    CKL();
+    CK(cudaMemcpyAsync(params_out, d_p, sizeof(double) * 6 * count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (p_soft_no_out) CK(cudaMemcpyAsync(p_soft_no_out, d_s, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_p); cudaFree(d_s);
+    return VX_OK;
+}
+
+int vx_dump_counts(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t count,
+                   int32_t *counts_out)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    rc = validate(ctx, cfg, false, nullptr);
+    if (rc) return rc;
+    if (count < 1 || !counts_out) return fail(ctx, VX_ERR_ARG, "bad output");
+    Job tmp;
+    tmp.cfg = *cfg; tmp.T = cfg->T; tmp.W = (cfg->T + 6) / 7; tmp.R = vx_host_rows(cfg->T);
+    int32_t *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(int32_t) * tmp.R * count));
+    rc = launch_dump(ctx, &tmp, first, count, nullptr, d, count);
+    if (rc == VX_OK) {
+        cudaError_t e = cudaMemcpyAsync(counts_out, d, sizeof(int32_t) * tmp.R * count, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = fail(ctx, VX_ERR_CUDA, "vx_dump_counts: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d);
+    return rc;
+}
+
+int vx_expected_series(vx_ctx *ctx, const vx_config *cfg, const double *params, int64_t n,
+                       double *series_out)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!cfg || !params || !series_out || n < 1) return fail(ctx, VX_ERR_ARG, "bad argument");
+    vx_config c = *cfg;
+    c.n_samples = n;
+    c.mode = VX_MODE_EXPECTED;
+    rc = validate(ctx, &c, true, params);
+    if (rc) return rc;
+    Job tmp;
+    tmp.cfg = c; tmp.T = c.T; tmp.W = (c.T + 6) / 7;
+    const int64_t RE = 4 * (int64_t)c.T + tmp.W, T = c.T;
+    double *d_p = nullptr, *d_o = nullptr;
+    CK(cudaMalloc(&d_p, sizeof(double) * 6 * n));
+    CK(cudaMalloc(&d_o, sizeof(double) * RE * n));
+    CK(cudaMemcpyAsync(d_p, params, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
+    SimArgs a = make_args(&tmp, 0, n, d_p);
+    vx_expected_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, d_o, n);
+    CKL();
+    std::vector<double> h(4 * T * n);
+    CK(cudaMemcpyAsync(h.data(), d_o, sizeof(double) * 4 * T * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_p); cudaFree(d_o);
+    for (int s = 0; s < 4; ++s)
+        for (int64_t t = 0; t < T; ++t)
+            for (int64_t i = 0; i < n; ++i)
+                series_out[((int64_t)s * n + i) * T + t] = h[((int64_t)s * T + t) * n + i];
+    return VX_OK;
+}
+
+// ---- self tests --------------------------------------------------------------------------
+int vx_test_philox(vx_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    uint32_t *d = nullptr;
+    CK(cudaMalloc(&d, 16));
+    vx_test_philox_kernel<<<1, 1, 0, ctx->stream>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
+    CKL();
+    CK(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return VX_OK;
+}
+
+int vx_test_poisson(vx_ctx *ctx, double lam, int64_t n, uint64_t seed, int32_t *out_host)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (n < 1 || !out_host) return fail(ctx, VX_ERR_ARG, "bad argument");
+    int32_t *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(int32_t) * n));
+    vx_test_poisson_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((float)lam, n, seed, d);
+    CKL();
+    CK(cudaMemcpyAsync(out_host, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return VX_OK;
+}
+
+int vx_test_normal(vx_ctx *ctx, int64_t n, uint64_t seed, float *out_host)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (n < 1 || !out_host) return fail(ctx, VX_ERR_ARG, "bad argument");
+    float *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(float) * n));
+    const int64_t pairs = (n + 1) / 2;
+    vx_test_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(n, seed, d);
+    CKL();
+    CK(cudaMemcpyAsync(out_host, d, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    return VX_OK;
+}
+
+int vx_test_select(vx_ctx *ctx, const int32_t *data, int64_t rows, int64_t n, const int64_t *ranks,
+                   int32_t n_ranks, int32_t *out, int64_t *sums)
+{
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (!data || rows < 1 || n < 1 || !ranks || n_ranks < 1 || n_ranks > SEL_MAXR || !out)
+        return fail(ctx, VX_ERR_ARG, "bad argument");
+    for (int k = 0; k < n_ranks; ++k)
+        if (ranks[k] < 0 || ranks[k] >= n) return fail(ctx, VX_ERR_ARG, "rank out of range");
+    int32_t *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(int32_t) * rows * n));
+    CK(cudaMemcpyAsync(d, data, sizeof(int32_t) * rows * n, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int64_t> rk(ranks, ranks + n_ranks), ord;
+    std::vector<long long> sm;
+    rc = run_select_i32(ctx, d, rows, n, n, rk, ord, sm);
+    cudaFree(d);
+    if (rc) return rc;
+    for (int64_t i = 0; i < rows * n_ranks; ++i) out[i] = (int32_t)ord[i];
+    if (sums) for (int64_t i = 0; i < rows; ++i) sums[i] = sm[i];
+    return VX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,676 @@
+// vaxmc_kernels.cuh -- sm_100a device code of the Monte Carlo hot path.
+//
+// What each kernel replaces in the reference (/root/reference/model.py):
+//   vx_param_stats_kernel   sample_param_combinations, rejection bookkeeping    :275-302
+//   vx_sim_kernel<..>       run_single_realization (day loop)                    :29-136
+//                           + the 30-day-shift/7-day-subsample weekly series     :196-214
+//                           + (FOLD) the per-date sum / rank counting that feeds :220-223
+//   vx_expected_kernel      run_single_realization with np.random.poisson := identity
+//   vx_select_kernel        np.quantile's order statistics + ndarray.mean sums   :220-223
+//   vx_extract_kernel       order statistics out of the merged window histograms
+//
+// Nothing here is a dense contraction: no tensor cores.  The stepper is instruction-issue
+// bound (Philox + sampler arithmetic, whole day loop in registers), the DUMP variant and the
+// select pass are HBM-bound streaming kernels.  See DESIGN.md.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vx {
+
+// ------------------------------------------------------------------ Philox4x32-10
+// Counter-based RNG (Salmon et al., SC'11).  key = job seed; counter =
+// (sample_lo, sample_hi, index, tag): a sample's stream depends only on its GLOBAL id, so
+// results are bit-identical however the sample range is sharded over GPUs.
+constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
+constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
+
+enum : uint32_t {
+    TAG_DAY = 0,     // index = day: 4 words -> Box-Muller pair + 2 inversion uniforms
+    TAG_PRO_ANTI = 1,// index = rejection attempt: p_pro, p_anti (2 x 53-bit)
+    TAG_PARAMS_A = 2,// pressure, tau
+    TAG_PARAMS_B = 3,// nv_0, nv_max
+    TAG_TEST = 7
+};
+
+__host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                                      uint32_t &c3, uint32_t k0, uint32_t k1)
+{
+#ifdef __CUDA_ARCH__
+    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), hi1 = __umulhi(PHILOX_M1, c2);
+#else
+    const uint32_t hi0 = (uint32_t)(((uint64_t)PHILOX_M0 * c0) >> 32);
+    const uint32_t hi1 = (uint32_t)(((uint64_t)PHILOX_M1 * c2) >> 32);
+#endif
+    const uint32_t lo0 = PHILOX_M0 * c0, lo1 = PHILOX_M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                        uint32_t c3, uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += PHILOX_W0; k1 += PHILOX_W1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// 53-bit uniform in [0,1) from two words, the construction numpy's legacy stream uses
+// (random_sample: (a>>5, b>>6) -> (a*2^26+b)/2^53), so lo+(hi-lo)*u has the same lattice as
+// np.random.uniform (model.py:277-294).
+__device__ __forceinline__ double u53(uint32_t a, uint32_t b)
+{
+    return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------ fast fp32 building blocks
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sqrt(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Two independent N(0,1) from two words (Box-Muller).  u1 in (0,1], angle in [-pi,pi).
+__device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, float &z0, float &z1)
+{
+    const float u1 = fmaf((float)w0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    // -2 ln(u1) = (-2 ln 2) * lg2(u1)
+    const float rad = fast_sqrt(fmaxf(-1.3862943611198906f * fast_lg2(u1), 0.0f));
+    const float ang = (float)(int32_t)w1 * 1.4629180792671596e-09f; // pi * 2^-31
+    z0 = rad * fast_cos(ang);
+    z1 = rad * fast_sin(ang);
+}
+
+// 1/k for the inversion recurrence p_k = p_{k-1} * lam / k
+__constant__ float c_rcp[72];
+
+// Poisson(lam) variate.
+//   lam == 0          -> 0 (numpy returns 0 without consuming the stream, model.py:104,116)
+//   0 < lam < 10      -> exact inversion by sequential search with one uniform (word w)
+//   lam >= 10         -> floor of the continuous inverse Q(z) of the Poisson CDF expanded
+//                        to O(1/lam) around the normal quantile z (Cornish-Fisher with the
+//                        lattice correction; Giles, ACM TOMS 42(1), 2016, eq. for Q_N1):
+//                          Q = lam + s z + (1/3 + z^2/6) + (-z/36 - z^3/72)/s
+//                              + (-8/405 + 7 z^2/810 + z^4/270)/lam,        s = sqrt(lam)
+//                        sup-CDF error vs the exact law <= 5.1e-5 at lam=10, 1.6e-5 at 16,
+//                        <1e-5 above 32 (tests/test_sampler_math.py computes these).
+__device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
+{
+    const float rs = fast_rsqrt(lam), s = lam * rs, z2 = z * z;
+    float q = fmaf(s, z, fmaf(z2, 0.16666667f, 0.33333334f));
+    q = fmaf(rs * z, fmaf(z2, -0.013888889f, -0.027777778f), q);
+    q = fmaf(rs * rs, fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f), q);
+    const float lf = floorf(lam);
+    int x = (int)lf + (int)floorf((lam - lf) + q);
+    x = max(x, 0);
+    if (lam < 10.0f) {
+        x = 0;
+        if (lam > 0.0f) {
+            const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
+            float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
+            while (u >= cdf && x < 64) {
+                ++x;
+                p *= lam * c_rcp[x];
+                cdf += p;
+            }
+        }
+    }
+    return x;
+}
+
+// ------------------------------------------------------------------ parameter draw
+struct SampleParams { double p_pro, p_anti, pressure, tau, nv0, nvmax; };
+
+// model.py:275-300 for ONE sample: redraw (p_pro,p_anti) until p_pro+p_anti <= 1, then the
+// other four.  Returns the number of rejections this sample consumed.
+__device__ __forceinline__ uint32_t draw_sample_params(const double *__restrict__ b, uint32_t k0,
+                                                       uint32_t k1, uint64_t sample,
+                                                       SampleParams &p, uint32_t max_attempts)
+{
+    const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32);
+    uint32_t j = 0;
+    for (;; ++j) {
+        const uint4 r = philox4x32_10(s_lo, s_hi, j, TAG_PRO_ANTI, k0, k1);
+        p.p_pro = b[0] + (b[1] - b[0]) * u53(r.x, r.y);
+        p.p_anti = b[2] + (b[3] - b[2]) * u53(r.z, r.w);
+        if (!(p.p_pro + p.p_anti > 1.0) || j + 1 >= max_attempts) break;
+    }
+    const uint4 ra = philox4x32_10(s_lo, s_hi, 0u, TAG_PARAMS_A, k0, k1);
+    const uint4 rb = philox4x32_10(s_lo, s_hi, 0u, TAG_PARAMS_B, k0, k1);
+    p.pressure = b[4] + (b[5] - b[4]) * u53(ra.x, ra.y);
+    p.tau = b[6] + (b[7] - b[6]) * u53(ra.z, ra.w);
+    p.nv0 = b[8] + (b[9] - b[8]) * u53(rb.x, rb.y);
+    p.nvmax = b[10] + (b[11] - b[10]) * u53(rb.z, rb.w);
+    return j;
+}
+
+struct Bounds { double b[12]; };
+
+// Rejection bookkeeping + moments of p_soft_no = 1-(p_pro+p_anti) (model.py:280-302,339-342)
+// over samples [first, first+count).  Per-block partials (deterministic tree), reduced by
+// vx_reduce_stats_kernel.  `stop` is a device flag/counter pair: [0] running total of
+// rejections (pushed every 64), [1] limit; when the total passes the limit every thread
+// bails out (the reference aborts at 10*n_rep rejections, model.py:283-287).
+__global__ void __launch_bounds__(256) vx_param_stats_kernel(Bounds bd, uint64_t seed,
+                                                             int64_t first, int64_t count,
+                                                             unsigned long long *stop,
+                                                             double *block_part /*[grid][3]*/)
+{
+    __shared__ double sh[3][256];
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    double rej = 0.0, s1 = 0.0, s2 = 0.0;
+    if (i < count) {
+        const uint64_t sample = (uint64_t)(first + i);
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+        const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32);
+        const unsigned long long limit = stop[1];
+        uint32_t j = 0, pending = 0;
+        double pro, anti;
+        bool bail = false;
+        for (;; ++j) {
+            const uint4 r = philox4x32_10(s_lo, s_hi, j, TAG_PRO_ANTI, k0, k1);
+            pro = bd.b[0] + (bd.b[1] - bd.b[0]) * u53(r.x, r.y);
+            anti = bd.b[2] + (bd.b[3] - bd.b[2]) * u53(r.z, r.w);
+            if (!(pro + anti > 1.0)) break;
+            if (++pending == 64) {
+                const unsigned long long t = atomicAdd(&stop[0], 64ull) + 64ull;
+                pending = 0;
+                if (t > limit) { bail = true; ++j; break; }
+            }
+            if (j == 0xfffffff0u) { bail = true; break; }
+        }
+        if (pending) atomicAdd(&stop[0], (unsigned long long)pending);
+        rej = (double)j;
+        if (!bail) {
+            const double s = 1 - (pro + anti);
+            s1 = s; s2 = s * s;
+        }
+    }
+    sh[0][threadIdx.x] = rej; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + off];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + off];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) block_part[(int64_t)blockIdx.x * 3 + threadIdx.x] = sh[threadIdx.x][0];
+}
+
+__global__ void __launch_bounds__(1024) vx_reduce_stats_kernel(const double *block_part,
+                                                               int64_t nblocks, double *out3)
+{
+    __shared__ double sh[3][1024];
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = threadIdx.x; i < nblocks; i += 1024)
+        for (int k = 0; k < 3; ++k) a[k] += block_part[i * 3 + k];
+    for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] = a[k];
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if (threadIdx.x < off)
+            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) out3[threadIdx.x] = sh[threadIdx.x][0];
+}
+
+// Parameter tuples as drawn on the device, for sample_param_combinations' return value.
+__global__ void __launch_bounds__(256) vx_sample_params_kernel(Bounds bd, uint64_t seed,
+                                                               int64_t first, int64_t count,
+                                                               double *params /*[count][6]*/,
+                                                               double *soft /*[count] or null*/)
+{
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= count) return;
+    SampleParams p;
+    draw_sample_params(bd.b, (uint32_t)seed, (uint32_t)(seed >> 32), (uint64_t)(first + i), p,
+                       1u << 20);
+    double *o = params + i * 6;
+    o[0] = p.p_pro; o[1] = p.p_anti; o[2] = p.pressure; o[3] = p.tau; o[4] = p.nv0; o[5] = p.nvmax;
+    if (soft) soft[i] = 1 - (p.p_pro + p.p_anti);
+}
+
+// ------------------------------------------------------------------------ stepper
+// Window descriptor of the streaming fold: values v with 0 <= v-a < len are histogrammed
+// at bin (v-a)>>shift into acc[hist + off + bin]; values v < a are counted.
+struct __align__(16) Win { int a; uint32_t len; uint32_t shift; uint32_t off; };
+
+struct SimArgs {
+    Bounds bd;
+    const double *params;   // explicit tuples [count][6] (then bd is unused) or nullptr
+    uint64_t seed;
+    int64_t first;          // GLOBAL id of local sample 0 (Philox counter)
+    int64_t count;          // samples in this launch
+    int64_t N;
+    int T, W;
+    int32_t *dump;          // DUMP: [R][dump_stride] raw rows, column = local sample
+    int64_t dump_stride;
+    const Win *wins;        // FOLD: [R][2]
+    unsigned long long *acc;// FOLD: header(8) | sums[R] | below[R][2] | hist bins
+};
+
+constexpr int ACC_HDR = 8;
+constexpr int WIN_DAYS = 14;       // one warp tile = 2 weeks = 14+14+2+2 = 32 rows
+constexpr int TILE_LD = 33;        // padded leading dimension: conflict-free both ways
+constexpr int SIM_THREADS = 256;
+
+enum { SIM_DUMP = 0, SIM_FOLD = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(SIM_THREADS, 4) vx_sim_kernel(const SimArgs a)
+{
+    __shared__ int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t warp_base = (int64_t)blockIdx.x * SIM_THREADS + warp * 32;
+    if (warp_base >= a.count) return;                       // warp-uniform
+    const int nvalid = (int)min((int64_t)32, a.count - warp_base);
+    const bool live = lane < nvalid;
+    const int64_t local = warp_base + (live ? lane : nvalid - 1);  // dead lanes shadow a live one
+    const uint64_t sample = (uint64_t)(a.first + local);
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32);
+    int *tile = tile_all + (MODE == SIM_FOLD ? warp * 32 * TILE_LD : 0);
+
+    SampleParams p;
+    if (a.params) {
+        const double *src = a.params + local * 6;
+        p.p_pro = src[0]; p.p_anti = src[1]; p.pressure = src[2];
+        p.tau = src[3]; p.nv0 = src[4]; p.nvmax = src[5];
+    } else {
+        draw_sample_params(a.bd.b, k0, k1, sample, p, 1u << 20);
+    }
+
+    // model.py:63-75.  int() truncates toward zero.
+    const double Nd = (double)a.N;
+    const double p_agn = 1 - (p.p_pro + p.p_anti);
+    int n_wait = (int)(p.p_pro * Nd);
+    int n_agn = (int)(p_agn * Nd);
+    int stock = 0, received = 0, n_vacc = 0;
+    const double tau7 = p.tau * 7;
+    const double ln2 = 0.6931471805599453;                 // np.log(2)
+    const bool monotone = (p.tau > 0.0) && (p.nv0 > 0.0);
+    bool capped = false;
+    const int arr_cap = (int)(p.nvmax * Nd);
+    const float c1 = (float)((2.0 / 7.0) / Nd);            // (2/7)/N   model.py:102
+    const float c2 = (float)(p.pressure / Nd);             // pressure/N model.py:112-115
+    int q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;            // delta_n_vacc of days = 5 (mod 7), 5 weeks deep
+
+    const int T = a.T, W = a.W;
+    for (int d0 = 0; d0 < T; d0 += WIN_DAYS) {
+#pragma unroll 1
+        for (int wk = 0; wk < 2; ++wk) {
+            const int dw = d0 + 7 * wk;
+            if (dw >= T) break;
+            // ---- weekly arrivals, model.py:69, 85-92 (fp64: the truncation must match)
+            int arr;
+            if (capped) {
+                arr = arr_cap;
+            } else {
+                const double g = p.nv0 * exp(ln2 * (double)dw / tau7);
+                const bool over = p.nvmax < g;              // Python min(g, nv_max)
+                arr = (int)((over ? p.nvmax : g) * Nd);
+                capped = over && monotone;
+            }
+            stock += arr; received += arr;
+            const int dend = min(7, T - dw);
+#pragma unroll 1
+            for (int dd = 0; dd < dend; ++dd) {
+                const int day = dw + dd;
+                const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)day, TAG_DAY, k0, k1);
+                float z1, z2;
+                normal_pair(r.x, r.y, z1, z2);
+                // ---- vaccination draw, model.py:102-112
+                const float lam1 = (float)n_wait * ((float)stock * c1);
+                int dv = poisson_draw(lam1, z1, r.z);
+                dv = min(dv, min(stock, n_wait));
+                n_vacc += dv; n_wait -= dv; stock -= dv;
+                // ---- conversion draw, model.py:115-120
+                const float lam2 = (float)n_agn * ((float)n_vacc * c2);
+                int da = poisson_draw(lam2, z2, r.w);
+                da = min(da, n_agn);
+                n_agn -= da; n_wait += da;
+                // ---- recording, model.py:124-127 and the weekly series :196-214
+                if (MODE == SIM_FOLD) {
+                    tile[(7 * wk + dd) * TILE_LD + lane] = n_vacc;
+                    tile[(14 + 7 * wk + dd) * TILE_LD + lane] = stock;
+                    if (dd == 0) {
+                        tile[(28 + wk) * TILE_LD + lane] = dv + q0;
+                        tile[(30 + wk) * TILE_LD + lane] = received;
+                    }
+                } else if (live) {
+                    const int64_t ld = a.dump_stride;
+                    a.dump[(int64_t)day * ld + local] = n_vacc;
+                    a.dump[((int64_t)T + 2 * W + day) * ld + local] = stock;
+                    if (dd == 0) {
+                        const int k = dw / 7;
+                        a.dump[((int64_t)T + k) * ld + local] = dv + q0;
+                        a.dump[((int64_t)T + W + k) * ld + local] = received;
+                    }
+                }
+                if (dd == 5) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dv; }
+            }
+        }
+        if (MODE == SIM_FOLD) {
+            // ---- fold: lane r owns tile row r (one date of one series) over the warp's samples
+            __syncwarp();
+            int grow = -1;
+            if (lane < 14) { const int d = d0 + lane; if (d < T) grow = d; }
+            else if (lane < 28) { const int d = d0 + lane - 14; if (d < T) grow = T + 2 * W + d; }
+            else if (lane < 30) { const int k = d0 / 7 + lane - 28; if (k < W) grow = T + k; }
+            else { const int k = d0 / 7 + lane - 30; if (k < W) grow = T + W + k; }
+            if (grow >= 0) {
+                const int R = 2 * T + 2 * W;
+                const Win wl = a.wins[grow * 2], wh = a.wins[grow * 2 + 1];
+                unsigned long long *hist = a.acc + ACC_HDR + 3 * (int64_t)R;
+                uint32_t sum = 0, clo = 0, chi = 0;
+                uint32_t rb_lo = 0xffffffffu, rc_lo = 0, rb_hi = 0xffffffffu, rc_hi = 0;
+                const int *row = tile + lane * TILE_LD;
+#pragma unroll 4
+                for (int s = 0; s < nvalid; ++s) {
+                    const int v = row[s];
+                    sum += (uint32_t)v;
+                    const int dl = v - wl.a, dh = v - wh.a;
+                    clo += (uint32_t)dl >> 31;
+                    chi += (uint32_t)dh >> 31;
+                    if ((uint32_t)dl < wl.len) {            // rare: run-length aggregated
+                        const uint32_t b = (uint32_t)dl >> wl.shift;
+                        if (b != rb_lo) {
+                            if (rc_lo) atomicAdd(hist + wl.off + rb_lo, (unsigned long long)rc_lo);
+                            rb_lo = b; rc_lo = 0;
+                        }
+                        ++rc_lo;
+                    }
+                    if ((uint32_t)dh < wh.len) {
+                        const uint32_t b = (uint32_t)dh >> wh.shift;
+                        if (b != rb_hi) {
+                            if (rc_hi) atomicAdd(hist + wh.off + rb_hi, (unsigned long long)rc_hi);
+                            rb_hi = b; rc_hi = 0;
+                        }
+                        ++rc_hi;
+                    }
+                }
+                if (rc_lo) atomicAdd(hist + wl.off + rb_lo, (unsigned long long)rc_lo);
+                if (rc_hi) atomicAdd(hist + wh.off + rb_hi, (unsigned long long)rc_hi);
+                atomicAdd(a.acc + ACC_HDR + grow, (unsigned long long)sum);
+                if (clo) atomicAdd(a.acc + ACC_HDR + R + 2 * grow, (unsigned long long)clo);
+                if (chi) atomicAdd(a.acc + ACC_HDR + R + 2 * grow + 1, (unsigned long long)chi);
+            }
+            __syncwarp();
+        }
+    }
+    if (MODE == SIM_FOLD && lane == 0)
+        atomicAdd(a.acc + 0, (unsigned long long)nvalid);  // header word 0: samples folded
+}
+
+// Expected-value stepper: np.random.poisson := identity, state carried in fp64 exactly as
+// Python carries it (model.py:29-136 with lam substituted for the draw).  One thread per
+// sample; rows [0,4T) are the four daily series in the reference's float units, rows
+// [4T,4T+W) the weekly series daily_pm[7k] + daily_pm[7k-30] (model.py:196-214).
+__global__ void __launch_bounds__(128) vx_expected_kernel(const SimArgs a, double *out,
+                                                          int64_t ld)
+{
+    const int64_t local = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (local >= a.count) return;
+    const uint64_t sample = (uint64_t)(a.first + local);
+    SampleParams p;
+    if (a.params) {
+        const double *src = a.params + local * 6;
+        p.p_pro = src[0]; p.p_anti = src[1]; p.pressure = src[2];
+        p.tau = src[3]; p.nv0 = src[4]; p.nvmax = src[5];
+    } else {
+        draw_sample_params(a.bd.b, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), sample, p, 1u << 20);
+    }
+    const double Nd = (double)a.N;
+    const double p_agn = 1 - (p.p_pro + p.p_anti);
+    double n_pro = (double)(int64_t)(p.p_pro * Nd);
+    double n_agn = (double)(int64_t)(p_agn * Nd);
+    double stock = 0, received = 0, n_vacc = 0;
+    double n_wait = n_pro - n_vacc;
+    const double ln2 = 0.6931471805599453;
+    const int T = a.T;
+    double q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
+    for (int day = 0; day < T; ++day) {
+        double arr = 0;
+        const int dd = day % 7;
+        if (dd == 0) {
+            const double g = p.nv0 * exp(ln2 * (double)day / (p.tau * 7));
+            const double m = (p.nvmax < g) ? p.nvmax : g;
+            arr = (double)(int64_t)(m * Nd);
+        }
+        stock += arr; received += arr;
+        const double avail = (2.0 / 7.0) * stock / Nd;
+        double dv = n_wait * avail;
+        if (stock < dv) dv = stock;
+        if (n_wait < dv) dv = n_wait;
+        n_vacc += dv; n_wait -= dv; stock -= dv;
+        const double f = n_vacc / Nd;
+        const double pc = f * p.pressure;
+        double da = n_agn * pc;
+        if (n_agn < da) da = n_agn;
+        n_agn -= da; n_wait += da;
+        const double dpm = dv * 1e6 / Nd;
+        out[(int64_t)day * ld + local] = f * 100;
+        out[((int64_t)T + day) * ld + local] = dpm;
+        out[((int64_t)2 * T + day) * ld + local] = received * 100 / Nd;
+        out[((int64_t)3 * T + day) * ld + local] = stock * 100 / Nd;
+        if (dd == 0) {
+            const double wkv = (day >= 30) ? dpm + q0 : dpm;
+            out[((int64_t)4 * T + day / 7) * ld + local] = wkv;
+        }
+        if (dd == 5) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dpm; }
+    }
+}
+
+// ------------------------------------------------------------- exact order statistics
+// One CTA per row of a [rows][ld] matrix.  Finds the order statistics at up to 8 ranks by
+// MSD radix select (8-bit digits, shared-memory histograms; ranks whose prefixes coincide
+// share a histogram) and the row sum.  Exact for any input: this is np.quantile's
+// partition step (model.py:220) done on integers / order-preserving keys.
+template <typename T> struct KeyTraits;
+template <> struct KeyTraits<int32_t> {
+    typedef uint32_t key_t; typedef long long sum_t;
+    static constexpr int BITS = 32;
+    __device__ static key_t to_key(int32_t v) { return (uint32_t)v ^ 0x80000000u; }
+    __device__ static int32_t from_key(key_t k) { return (int32_t)(k ^ 0x80000000u); }
+    __device__ static sum_t to_sum(int32_t v) { return (long long)v; }
+};
+template <> struct KeyTraits<double> {
+    typedef unsigned long long key_t; typedef double sum_t;
+    static constexpr int BITS = 64;
+    __device__ static key_t to_key(double v) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+        return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+    }
+    __device__ static double from_key(key_t k) {
+        const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+        return __longlong_as_double((long long)b);
+    }
+    __device__ static sum_t to_sum(double v) { return v; }
+};
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_MAXR = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
+    const T *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks,
+    int nranks, T *__restrict__ out /*[rows][nranks]*/,
+    typename KeyTraits<T>::sum_t *__restrict__ sums /*[rows]*/)
+{
+    typedef KeyTraits<T> KT;
+    typedef typename KT::key_t key_t;
+    typedef typename KT::sum_t sum_t;
+    __shared__ uint32_t hist[SEL_MAXR][256];
+    __shared__ key_t prefix[SEL_MAXR], dprefix[SEL_MAXR];
+    __shared__ long long rem[SEL_MAXR];
+    __shared__ int hid[SEL_MAXR];
+    __shared__ int ndist;
+    __shared__ sum_t red_sum[SEL_THREADS];
+    __shared__ key_t red_xor[SEL_THREADS];
+
+    const T *row = data + (int64_t)blockIdx.x * ld;
+    const int tid = threadIdx.x;
+
+    // pass 0: row sum (fixed-order tree -> deterministic) and the bits that vary in the row
+    sum_t acc = 0;
+    key_t diff = 0;
+    const key_t first_key = KT::to_key(row[0]);
+    for (int64_t i = tid; i < n; i += SEL_THREADS) {
+        const T v = row[i];
+        acc += KT::to_sum(v);
+        diff |= KT::to_key(v) ^ first_key;
+    }
+    red_sum[tid] = acc; red_xor[tid] = diff;
+    __syncthreads();
+    for (int off = SEL_THREADS / 2; off > 0; off >>= 1) {
+        if (tid < off) { red_sum[tid] += red_sum[tid + off]; red_xor[tid] |= red_xor[tid + off]; }
+        __syncthreads();
+    }
+    if (tid == 0 && sums) sums[blockIdx.x] = red_sum[0];
+    diff = red_xor[0];
+    // keys agree above bit `top`: those bits go straight into the prefix
+    int top = 0;
+    if (diff) top = (KT::BITS == 64) ? 64 - __clzll((long long)diff) : 32 - __clz((int)(uint32_t)diff);
+    const int npass = (top + 7) / 8;
+    if (tid < nranks) {
+        rem[tid] = ranks[tid];
+        prefix[tid] = (npass * 8 >= KT::BITS) ? (key_t)0 : (first_key >> (npass * 8));
+    }
+    __syncthreads();
+
+    for (int pass = npass - 1; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        if (tid == 0) {
+            int nd = 0;
+            for (int k = 0; k < nranks; ++k) {
+                int f = -1;
+                for (int d = 0; d < nd; ++d) if (dprefix[d] == prefix[k]) { f = d; break; }
+                if (f < 0) { f = nd; dprefix[nd++] = prefix[k]; }
+                hid[k] = f;
+            }
+            ndist = nd;
+        }
+        for (int i = tid; i < SEL_MAXR * 256; i += SEL_THREADS) (&hist[0][0])[i] = 0;
+        __syncthreads();
+        const int nd = ndist;
+        const bool whole = (shift + 8 >= KT::BITS);
+        for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+            const int64_t i = i0 + tid;
+            const bool in = i < n;
+            key_t key = 0, hi = 0;
+            uint32_t bin = 0;
+            if (in) {
+                key = KT::to_key(row[i]);
+                hi = whole ? (key_t)0 : (key >> (shift + 8));
+                bin = (uint32_t)(key >> shift) & 255u;
+            }
+            for (int d = 0; d < nd; ++d) {
+                const bool hit = in && (hi == dprefix[d]);
+                // warp-aggregate the common all-lanes-same-bin case (flat rows)
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m == 0) continue;
+                const int leader = __ffs(m) - 1;
+                const uint32_t lbin = __shfl_sync(0xffffffffu, bin, leader);
+                const uint32_t same = __ballot_sync(0xffffffffu, hit && bin == lbin);
+                if (same == m) {
+                    if ((tid & 31) == leader) atomicAdd(&hist[d][lbin], (uint32_t)__popc(m));
+                } else if (hit) {
+                    atomicAdd(&hist[d][bin], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < nranks) {
+            const uint32_t *h = hist[hid[tid]];
+            long long r = rem[tid], cum = 0;
+            int b = 0;
+            for (; b < 255; ++b) {
+                if (r < cum + (long long)h[b]) break;
+                cum += h[b];
+            }
+            rem[tid] = r - cum;
+            prefix[tid] = (prefix[tid] << 8) | (key_t)b;
+        }
+        __syncthreads();
+    }
+    if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(prefix[tid]);
+}
+
+// --------------------------------------------- order statistics out of merged windows
+// One warp per (row, window).  tgt[(row*2+w)*2 + {0,1}] = global ranks served by the window
+// (-1: none).  res gets, per target, (status << 32) | bin with status 0 found, 1 the rank
+// lies below the window (rank < #values < a), 2 above it.
+__global__ void __launch_bounds__(256) vx_extract_kernel(const unsigned long long *__restrict__ acc,
+                                                         const Win *__restrict__ wins,
+                                                         const long long *__restrict__ tgt,
+                                                         long long *__restrict__ res, int R)
+{
+    const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= 2 * R) return;
+    const Win w = wins[gw];
+    const uint32_t nb = w.len >> w.shift;
+    const unsigned long long *hist = acc + ACC_HDR + 3 * (int64_t)R + w.off;
+    const long long below = (long long)acc[ACC_HDR + R + gw];
+    long long t[2] = {tgt[gw * 2], tgt[gw * 2 + 1]};
+    long long r[2] = {-1, -1};
+    for (int k = 0; k < 2; ++k)
+        if (t[k] >= 0 && t[k] < below) { r[k] = (1ll << 32); t[k] = -1; }
+    long long cum = below;
+    for (uint32_t b0 = 0; b0 < nb && (t[0] >= 0 || t[1] >= 0); b0 += 32) {
+        const uint32_t b = b0 + lane;
+        long long h = (b < nb) ? (long long)hist[b] : 0;
+        long long inc = h;                                   // inclusive warp scan
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long y = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const long long c_incl = cum + inc;
+        for (int k = 0; k < 2; ++k) {
+            if (t[k] < 0) continue;
+            const uint32_t m = __ballot_sync(0xffffffffu, t[k] < c_incl);
+            if (m) { r[k] = (long long)(b0 + (uint32_t)(__ffs(m) - 1)); t[k] = -1; }
+        }
+        cum = __shfl_sync(0xffffffffu, c_incl, 31);
+    }
+    for (int k = 0; k < 2; ++k)
+        if (t[k] >= 0) r[k] = (2ll << 32);
+    if (lane == 0) { res[gw * 2] = r[0]; res[gw * 2 + 1] = r[1]; }
+}
+
+// ------------------------------------------------------------------- self-test kernels
+__global__ void vx_test_philox_kernel(uint4 ctr, uint2 key, uint32_t *out)
+{
+    const uint4 r = philox4x32_10(ctr.x, ctr.y, ctr.z, ctr.w, key.x, key.y);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+
+__global__ void vx_test_poisson_kernel(float lam, int64_t n, uint64_t seed, int32_t *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0u, TAG_TEST, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+    float z1, z2;
+    normal_pair(r.x, r.y, z1, z2);
+    out[i] = poisson_draw(lam, (i & 1) ? z2 : z1, (i & 1) ? r.w : r.z);
+}
+
+__global__ void vx_test_normal_kernel(int64_t n, uint64_t seed, float *out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * i >= n) return;
+    const uint4 r = philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 1u, TAG_TEST, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+    float z1, z2;
+    normal_pair(r.x, r.y, z1, z2);
+    out[2 * i] = z1;
+    if (2 * i + 1 < n) out[2 * i + 1] = z2;
+}
+
+} // namespace vx

@@ -1,0 +1,140 @@
+"""One process per GPU: shard the Monte Carlo sample range over ranks and merge with NCCL.
+
+The path shards by independent units: every sample is independent
+(model.py:176-179) and its Philox stream is keyed by its GLOBAL id, so rank r simply folds
+the contiguous range shard_range(n, r, world).  The only exchange steps are
+
+  1. one all-reduce(sum) of four float64 (rejection count and the moments of p_soft_no,
+     model.py:280-287, 339-342), and
+  2. per streaming pass, one all-reduce(sum) of the int64 accumulator slab (per-date sums,
+     counts below the windows, window histograms) -- integer addition, hence results that
+     are bit-identical for 1/2/4/8 GPUs.
+
+torch.distributed is plumbing only (process group + the NCCL call on a tensor that aliases
+the library's device slab); all arithmetic is in libvaxmc.so.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from . import _native as nat
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous [first, first+count) of global sample ids owned by `rank`."""
+    base, rem = divmod(int(n), int(world))
+    first = rank * base + min(rank, rem)
+    count = base + (1 if rank < rem else 0)
+    return first, count
+
+
+class _DevicePtr:
+    """Exposes a raw device pointer through __cuda_array_interface__ (tensor handoff)."""
+
+    def __init__(self, ptr: int, n_words: int):
+        self.__cuda_array_interface__ = {
+            "shape": (n_words,), "typestr": "<i8", "data": (ptr, False), "version": 3,
+            "strides": None,
+        }
+
+
+class ContextEngine:
+    """Adapter: a libvaxmc Context as the engine run_sharded drives."""
+
+    def __init__(self, ctx: nat.Context):
+        self.ctx = ctx
+
+    def begin(self, cfg, first, count):
+        self.ctx.job_begin(cfg, first, count)
+
+    def param_stats(self) -> np.ndarray:
+        return self.ctx.job_param_stats()
+
+    def set_param_stats(self, st) -> bool:
+        return self.ctx.job_set_param_stats(st)
+
+    def pilot(self):
+        self.ctx.job_pilot()
+
+    def is_direct(self) -> bool:
+        return self.ctx.job_is_direct()
+
+    def accumulate(self):
+        self.ctx.job_accumulate()
+
+    def acc_tensor(self):
+        import torch
+
+        ptr, n = self.ctx.job_acc()
+        if n == 0:
+            return None
+        return torch.as_tensor(_DevicePtr(ptr, n), device=f"cuda:{self.ctx.device}")
+
+    def finalize(self, out) -> int:
+        return self.ctx.job_finalize(out)
+
+    def end(self):
+        self.ctx.job_end()
+
+    def stats_tensor(self, st: np.ndarray):
+        import torch
+
+        return torch.from_numpy(st).to(f"cuda:{self.ctx.device}")
+
+
+def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out):
+    """Drive one rank of a sharded job.  `all_reduce(tensor)` sums in place across ranks."""
+    first, count = shard_range(cfg.n_samples, rank, world)
+    engine.begin(cfg, first, count)
+    try:
+        st = engine.param_stats()
+        t = engine.stats_tensor(st)
+        all_reduce(t)
+        st = t.cpu().numpy().astype(np.float64)
+        out = make_out()
+        if engine.set_param_stats(st):
+            out.c.aborted = 1
+            out.c.n_rejected = int(st[0])
+            return out
+        engine.pilot()
+        for _ in range(64):
+            engine.accumulate()
+            acc = engine.acc_tensor()
+            if acc is not None:
+                all_reduce(acc)
+            rc = engine.finalize(out)
+            if rc != nat.VX_REFINE:
+                return out
+        raise RuntimeError("window refinement did not converge")
+    finally:
+        engine.end()
+
+
+def run_job(cfg, device=None):
+    """Whole job for run_model: sharded when launched under torchrun, single GPU otherwise."""
+    world = 1
+    dist = None
+    try:
+        import torch.distributed as dist_mod
+
+        if dist_mod.is_available() and dist_mod.is_initialized():
+            dist = dist_mod
+            world = dist.get_world_size()
+    except ImportError:
+        pass
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
+    ctx = nat.default_context(int(device))
+    if world == 1:
+        return ctx.run_bounds(cfg)
+    import torch
+
+    def all_reduce(t):
+        torch.cuda.current_stream(t.device).synchronize()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream(t.device).synchronize()
+
+    return run_sharded(ContextEngine(ctx), cfg, dist.get_rank(), world, all_reduce,
+                       lambda: nat.ResultBuffers(cfg.T))

@@ -1,0 +1,427 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bars (BASELINE.json north_star):
+  (1) expected-value mode vs the oracle/reference          <= 1e-5 relative (we see ~1e-15)
+  (2) stochastic mode on identical parameter tuples         two-sample KS per week
+  (3) integer results                                       bit-exact (order statistics, sums,
+                                                            direct vs streamed, 1 vs k shards)
+Everything deterministic given the parameters (arrivals -> `received` rows) is bit-exact
+against the oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy import stats
+
+import philox_ref as pr
+import ref_oracle as ro
+from conftest import USA_DATES, usa_bounds_frac, wide_bounds_frac
+
+pytestmark = pytest.mark.gpu
+
+SERIES = ro.SERIES
+USA_T, USA_W = 564, 81
+
+
+def _cfg(vax, bounds, n, seed=12345, T=USA_T, N=50000, q=(0.025, 0.975), **kw):
+    return vax._native.make_config(bounds, N, T, n, seed, q[0], q[1], **kw)
+
+
+# ------------------------------------------------------------------ building blocks
+def test_philox_known_answers(ctx):
+    for c, k, e in pr.KAT:
+        assert ctx.test_philox(c, k) == list(e)
+
+
+def test_device_parameter_draw_matches_numpy_restatement(vax, ctx):
+    for bounds, seed in ((usa_bounds_frac(), 12345), (wide_bounds_frac(), 7),
+                         (np.array([0.5, 0.9, 0.3, 0.6, 0.0, 0.1, 3, 4, 0.002, 0.0024, 0.1, 0.1]), 99)):
+        cfg = _cfg(vax, bounds, 5000, seed=seed)
+        params, soft = ctx.sample_params(cfg, 1000, 5000)
+        ep, es, rej = pr.draw_params(bounds, seed, 1000, 5000)
+        assert np.array_equal(params, ep)
+        assert np.array_equal(soft, es)
+        assert (params[:, 0] + params[:, 1] <= 1.0).all()
+        # rejection bookkeeping (model.py:280-287) and p_soft_no moments (model.py:339-342)
+        ctx.job_begin(cfg, 1000, 4000)
+        st = ctx.job_param_stats()
+        ctx.job_end()
+        assert st[0] == rej[:4000].sum() and st[3] == 4000
+        assert np.isclose(st[1], es[:4000].sum(), rtol=1e-13)
+        assert np.isclose(st[2], (es[:4000] ** 2).sum(), rtol=1e-13)
+
+
+def test_rejection_abort_semantics(vax):
+    # model.py:283-287: more than 10*n_rep rejections -> (None, None)
+    res, err, msg = vax.run_model([70, 90], [50, 60], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10], 95, 50,
+                                  50000, USA_DATES, seed=3)
+    assert res is None and msg == "Agnosticts: "
+    assert err == ro.ERR_BOUNDS
+    p, s = vax.sample_param_combinations([0.7, 0.9], [0.5, 0.6], [0, 0.1], [3, 4], [0.002, 0.0024],
+                                         [0.1, 0.1], 5, seed=3)
+    assert p is None and s is None
+    # feasible but with rejections: accepted tuples all satisfy the constraint
+    p, s = vax.sample_param_combinations([0.5, 0.9], [0.3, 0.6], [0, 0.1], [3, 4], [0.002, 0.0024],
+                                         [0.1, 0.1], 40, seed=2)
+    assert len(p) == 40 and all(a + b <= 1.0 for a, b, *_ in p)
+    assert np.allclose(s, [1 - (a + b) for a, b, *_ in p], rtol=0, atol=0)
+
+
+@pytest.mark.parametrize("lam", [0.0, 1e-3, 0.5, 3.0, 9.999, 10.0, 10.5, 16.0, 63.0, 300.0, 2857.0,
+                                 1e4, 1e5])
+def test_poisson_sampler_law(ctx, lam):
+    """Chi-square goodness of fit of the device sampler against the exact Poisson pmf."""
+    n = 2_000_000
+    x = ctx.test_poisson(lam, n, seed=2024 + int(lam * 1000) % 9973).astype(np.int64)
+    if lam == 0.0:
+        assert (x == 0).all()
+        return
+    assert abs(x.mean() - lam) < 5 * np.sqrt(lam / n) + 1e-6 * lam
+    assert abs(x.var() - lam) < 6 * lam * np.sqrt(2.0 / n) + 6 * np.sqrt(lam / n) + 2e-6 * lam * lam
+    lo = max(int(stats.poisson.ppf(1e-5, lam)), 0)
+    hi = int(stats.poisson.ppf(1 - 1e-5, lam)) + 1
+    edges = np.arange(lo, hi + 1)
+    # merge to at most ~200 cells with expected count >= 50
+    cdf = stats.poisson.cdf(edges - 1, lam)
+    step = max(1, len(edges) // 200)
+    edges = edges[::step]
+    cdf = stats.poisson.cdf(edges - 1, lam)
+    probs = np.diff(np.concatenate([[0.0], cdf[1:], [1.0]]))
+    obs = np.histogram(x, bins=np.concatenate([[-0.5], edges[1:] - 0.5, [np.inf]]))[0]
+    keep = probs * n >= 50
+    probs_k = np.concatenate([probs[keep], [probs[~keep].sum()]])
+    obs_k = np.concatenate([obs[keep], [obs[~keep].sum()]])
+    if probs_k[-1] * n < 5:
+        probs_k[-2] += probs_k[-1]; obs_k[-2] += obs_k[-1]
+        probs_k, obs_k = probs_k[:-1], obs_k[:-1]
+    chi2 = ((obs_k - n * probs_k) ** 2 / (n * probs_k)).sum()
+    p = stats.chi2.sf(chi2, len(probs_k) - 1)
+    assert p > 1e-4, (lam, chi2, len(probs_k), p)
+
+
+def test_normal_pair_law(ctx):
+    z = ctx.test_normal(4_000_000, seed=5).astype(np.float64)
+    assert abs(z.mean()) < 5 / np.sqrt(len(z))
+    assert abs(z.var() - 1) < 5 * np.sqrt(2 / len(z))
+    assert stats.kstest(z[:1_000_000], "norm").pvalue > 1e-3
+    # the two normals of one Box-Muller pair are uncorrelated
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 5 / np.sqrt(len(z) / 2)
+    assert np.abs(z).max() < 7.0
+
+
+def test_radix_select_exact(ctx):
+    rng = np.random.default_rng(1)
+    n = 70001
+    data = np.stack([
+        rng.integers(0, 350000, n), rng.integers(0, 5, n), np.zeros(n, dtype=np.int64),
+        np.full(n, 2**27 - 1), rng.poisson(3000, n), np.arange(n)[::-1],
+        (rng.random(n) < 0.3) * rng.integers(0, 1 << 26, n), rng.integers(0, 2, n) * 50000,
+    ]).astype(np.int32)
+    ranks = [0, 1, 1750, 1751, n // 2, n - 2, n - 1, 68250]
+    got, sums = ctx.test_select(data, ranks)
+    want = np.sort(data, axis=1)[:, ranks]
+    assert np.array_equal(got, want)
+    assert np.array_equal(sums, data.astype(np.int64).sum(axis=1))
+    # tiny rows
+    for m in (1, 2, 31, 33, 513):
+        d = rng.integers(0, 1000, (3, m)).astype(np.int32)
+        rk = sorted({0, m // 2, m - 1})
+        got, sums = ctx.test_select(d, rk)
+        assert np.array_equal(got, np.sort(d, axis=1)[:, rk])
+
+
+# ------------------------------------------------------ (1) expected-value parity
+def test_expected_single_realizations_vs_golden_and_oracle(vax, ctx, golden_dir):
+    g = np.load(os.path.join(golden_dir, "single_realizations.npz"))
+    plist = g["params"]
+    worst = 0.0
+    for T, N in ((564, 50000), (100, 1000), (1826, 1000000)):
+        cfg = _cfg(vax, np.zeros(12), len(plist), T=T, N=N)
+        got = ctx.expected_series(cfg, plist)            # [4][n][T]
+        for i in range(len(plist)):
+            want = g[f"exp/{i}/{T}/{N}"]                  # reference itself, [4][T]
+            orc = ro.run_single_realization(None, 1, plist[i], T, N)
+            for s, k in enumerate(SERIES):
+                assert np.array_equal(orc[k], want[s])
+                err = np.abs(got[s, i] - want[s]) / np.maximum(np.abs(want[s]), 1e-300)
+                err[want[s] == 0] = np.abs(got[s, i])[want[s] == 0]
+                worst = max(worst, err.max())
+    assert worst <= 1e-5, worst           # north_star tolerance
+    assert worst <= 1e-12, worst          # what fp64 state actually delivers
+
+
+@pytest.mark.parametrize("name", ["usa_expected_seed12345_ci95_n100.npz",
+                                  "wide5y_expected_seed7_ci90_n32_N1e6.npz"])
+def test_expected_run_sampling_vs_reference_fixture(vax, golden_dir, name):
+    """run_sampling over the reference's own parameter tuples, expected-value mode: mean and
+    both quantile bands against the reference's output (tolerance 1e-5 relative)."""
+    g = np.load(os.path.join(golden_dir, name))
+    res = vax.run_sampling(g["params"], str(g["start_date"]), str(g["end_date"]), float(g["CI"]) / 100,
+                           int(g["N"]), mode="expected")
+    assert res["number_finished_samples"] == int(g["number_finished_samples"])
+    for k in SERIES:
+        for f in ("mean", "lower", "upper"):
+            want = g[f"{k}/{f}"]
+            got = res[k][f]
+            assert got.shape == want.shape
+            assert np.allclose(got, want, rtol=1e-5, atol=1e-9), (k, f)
+            assert np.allclose(got, want, rtol=1e-11, atol=1e-12), (k, f)
+        assert [str(x) for x in res[k]["dates"]] == list(g[f"{k}/dates"])
+
+
+# ------------------------------------------- (2)/(3) stochastic mode, same parameters
+def _oracle_rows(daily, weekly, T, W):
+    """oracle bulk_counts -> the engine's raw-row layout [R][n]."""
+    n_vacc, received, stock = daily
+    return np.concatenate([n_vacc, weekly, received[0::7][:W], stock], axis=0)
+
+
+def test_deterministic_rows_bit_exact_and_invariants(vax, ctx):
+    bounds = usa_bounds_frac()
+    n = 4096
+    cfg = _cfg(vax, bounds, n, seed=77)
+    params, _ = ctx.sample_params(cfg, 0, n)
+    out, counts = ctx.run_params(cfg, params, want_counts=True)
+    T, W = USA_T, USA_W
+    n_vacc, dose, recv_w, stock = counts[:T], counts[T:T + W], counts[T + W:T + 2 * W], counts[T + 2 * W:]
+    # `received` is a deterministic function of the tuple (model.py:69, 85-92): bit-exact
+    d, w = ro.bulk_counts(5, params, T, 50000, threads=8)
+    assert np.array_equal(recv_w, d[1][0::7][:W])
+    recv_d = np.repeat(recv_w, 7, axis=0)[:T]
+    assert np.array_equal(n_vacc + stock, recv_d)                 # dose conservation
+    assert (np.diff(n_vacc, axis=0) >= 0).all()
+    n_pro = (params[:, 0] * 50000).astype(np.int64)
+    n_agn = ((1 - (params[:, 0] + params[:, 1])) * 50000).astype(np.int64)
+    assert (n_vacc[-1] <= n_pro + n_agn).all()
+    dv = np.diff(n_vacc, axis=0, prepend=0)
+    wk = dv[0::7][:W].copy()
+    wk[5:] += dv[5::7][:W - 5]                                    # dv[7k] + dv[7k-30]
+    assert np.array_equal(dose, wk)
+    # bounds-mode dump of the same global ids is the same integers
+    assert np.array_equal(ctx.dump_counts(cfg, 0, n), counts)
+    assert np.array_equal(ctx.dump_counts(cfg, 1000, 500), counts[:, 1000:1500])
+
+
+def test_direct_reduction_equals_numpy_on_the_same_integers(vax, ctx):
+    """Order statistics, lerp and mean: the engine vs np.quantile/mean (model.py:220-223) on
+    the very trajectories it simulated (bit-exact bands, mean to 1e-13)."""
+    for bounds, T, N, q, n in ((usa_bounds_frac(), USA_T, 50000, (0.025, 0.975), 1000),
+                               (usa_bounds_frac(), USA_T, 50000, (0.49525, 0.50475), 100),
+                               (wide_bounds_frac(), 1826, 1000000, (0.005, 0.995), 257),
+                               (usa_bounds_frac(), 30, 333, (0.0, 1.0), 7),
+                               (usa_bounds_frac(), 8, 50000, (0.25, 0.75), 1)):
+        W = (T + 6) // 7
+        cfg = _cfg(vax, bounds, n, seed=11, T=T, N=N, q=q)
+        params, _ = ctx.sample_params(cfg, 0, n)
+        out, counts = ctx.run_params(cfg, params, want_counts=True)
+        c = counts.astype(np.int64)
+        vals = [(c[:T] / N) * 100, c[T:T + W] * 1e6 / N,
+                np.repeat(c[T + W:T + 2 * W], 7, axis=0)[:T] * 100 / N, c[T + 2 * W:] * 100 / N]
+        for s in range(4):
+            qq = np.quantile(vals[s], [q[0], q[1]], axis=1)
+            assert np.array_equal(out.lower[s], qq[0]), (T, N, s)
+            assert np.array_equal(out.upper[s], qq[1]), (T, N, s)
+            assert np.allclose(out.mean[s], vals[s].mean(axis=1), rtol=1e-13, atol=1e-13)
+        # run_bounds on the same seed draws the same tuples itself
+        ob = ctx.run_bounds(cfg)
+        for s in range(4):
+            assert np.array_equal(ob.lower[s], out.lower[s]) and np.array_equal(ob.upper[s], out.upper[s])
+            assert np.array_equal(ob.mean[s], out.mean[s])
+
+
+def test_ks_per_week_against_oracle_on_identical_parameters(vax, ctx):
+    """north_star check (2): identical sampled parameter sets, matched sample counts, two-sample
+    KS per weekly date and series between the CUDA path and the numpy-law oracle."""
+    bounds = usa_bounds_frac()
+    n = 60000
+    cfg = _cfg(vax, bounds, n, seed=4242)
+    params, _ = ctx.sample_params(cfg, 0, n)
+    counts = ctx.dump_counts(cfg, 0, n)
+    d, w = ro.bulk_counts(987, params, USA_T, 50000, threads=os.cpu_count())
+    orc = _oracle_rows(d, w, USA_T, USA_W)
+    T, W = USA_T, USA_W
+    rows = {"n_vacc": np.arange(0, T, 7), "dose": T + np.arange(W), "stock": T + 2 * W + np.arange(0, T, 7)}
+    pvals = []
+    for name, rr in rows.items():
+        for r in rr:
+            a, b = counts[r], orc[r]
+            if np.array_equal(np.unique(a), np.unique(b)) and len(np.unique(a)) == 1:
+                continue
+            pvals.append(stats.ks_2samp(a, b, method="asymp").pvalue)
+    pvals = np.array(pvals)
+    assert len(pvals) > 200
+    assert pvals.min() > 0.01 / len(pvals), pvals.min()           # Bonferroni: no week rejects
+    assert (pvals < 0.01).mean() <= 0.03, (pvals < 0.01).mean()   # chance level of p<0.01
+    assert stats.kstest(pvals, "uniform").pvalue > 1e-4 or np.median(pvals) > 0.3
+    # the per-sample difference has zero mean within Monte Carlo error (same tuples -> paired)
+    for r in (100, 300, 563, T + 20, T + 60, T + 2 * W + 300):
+        diff = counts[r].astype(np.float64) - orc[r]
+        assert abs(diff.mean()) < 5 * diff.std() / np.sqrt(n) + 1e-9, r
+
+
+def test_bands_agree_with_reference_fixture_within_mc_error(vax, golden_dir):
+    """The reference's own seeded run (n=100, CI=95): our bands at n=20000 must be compatible."""
+    g = np.load(os.path.join(golden_dir, "usa_seed12345_ci95_n100.npz"))
+    res, err, msg = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95, 20000,
+                                  50000, USA_DATES, seed=12345)
+    assert err == "" and msg == "Agnosticts: 37 - 46%"
+    assert msg == str(g["msg_agnostics_pct"])
+    for k in SERIES:
+        spread = np.maximum(res[k]["upper"] - res[k]["lower"], 1e-9)
+        # mean of 100 samples scatters by ~ spread/4/sqrt(100); allow 5 sigma
+        assert (np.abs(res[k]["mean"] - g[f"{k}/mean"]) < 5 * spread / 4 / 10 + 1e-9).mean() > 0.97, k
+        assert [str(x) for x in res[k]["dates"]] == list(g[f"{k}/dates"])
+        assert res[k]["mean"].shape == g[f"{k}/mean"].shape
+
+
+# --------------------------------------- (3) streamed == direct, sharding invariance
+def _run(vax, ctx, bounds, n, seed, direct_max, T=USA_T, N=50000, q=(0.025, 0.975), pilot=0):
+    cfg = _cfg(vax, bounds, n, seed=seed, T=T, N=N, q=q, direct_max=direct_max, pilot_samples=pilot)
+    return ctx.run_bounds(cfg)
+
+
+def _same(a, b):
+    for s in range(4):
+        if not (np.array_equal(a.lower[s], b.lower[s]) and np.array_equal(a.upper[s], b.upper[s])
+                and np.array_equal(a.mean[s], b.mean[s])):
+            return False
+    return a.c.n_finished == b.c.n_finished
+
+
+@pytest.mark.parametrize("q", [(0.025, 0.975), (0.49525, 0.50475), (0.0, 1.0), (0.001, 0.9999)])
+def test_streamed_equals_direct(vax, ctx, q):
+    bounds = usa_bounds_frac()
+    n = 50000
+    direct = _run(vax, ctx, bounds, n, 31, direct_max=1 << 20, q=q)
+    assert direct.c.n_passes == 0
+    streamed = _run(vax, ctx, bounds, n, 31, direct_max=1, q=q, pilot=8192)
+    assert streamed.c.n_passes >= 1
+    assert _same(direct, streamed)
+
+
+def test_streamed_refinement_paths(vax, ctx):
+    """Tiny windows / no pilot / degenerate bounds force the VX_REFINE loop; still exact."""
+    bounds = usa_bounds_frac()
+    n = 20000
+    direct = _run(vax, ctx, bounds, n, 5, direct_max=1 << 20)
+    try:
+        ctx.set_option("max_bins", 16)
+        a = _run(vax, ctx, bounds, n, 5, direct_max=1, pilot=4096)
+        assert a.c.n_passes >= 2 and _same(direct, a)
+        ctx.set_option("use_pilot", 0)
+        b = _run(vax, ctx, bounds, n, 5, direct_max=1)
+        assert b.c.n_passes >= 3 and _same(direct, b)
+        ctx.set_option("max_bins", 65536)
+        c = _run(vax, ctx, bounds, n, 5, direct_max=1)
+        assert c.c.n_passes >= 2 and _same(direct, c)
+        ctx.set_option("use_pilot", 1)
+        ctx.set_option("pilot_sigmas", 0.0)     # windows too narrow: ranks fall outside
+        d = _run(vax, ctx, bounds, n, 5, direct_max=1, pilot=2048)
+        assert d.c.n_passes >= 2 and _same(direct, d)
+    finally:
+        ctx.set_option("max_bins", 65536); ctx.set_option("use_pilot", 1); ctx.set_option("pilot_sigmas", 6.0)
+    # single-value bounds ([v, v], model.py:376-377): every sample has the same tuple
+    deg = np.array([0.4, 0.4, 0.2, 0.2, 0.01, 0.01, 6, 6, 0.011, 0.011, 0.07, 0.07])
+    d0 = _run(vax, ctx, deg, 30000, 9, direct_max=1 << 20)
+    d1 = _run(vax, ctx, deg, 30000, 9, direct_max=1, pilot=4096)
+    assert _same(d0, d1)
+    assert np.array_equal(d0.lower[2], d0.upper[2])       # deliveries are deterministic here
+
+
+def test_sharding_is_bit_exact(vax, ctx):
+    """1 vs 2 vs 3 vs 8 shards of the same global sample range, merged by integer addition
+    (what the NCCL all-reduce does across GPUs): identical bytes out."""
+    import torch
+
+    nat = vax._native
+    from importlib import import_module
+    dist = import_module("covid19-vaccination-model_b200.distributed")
+    bounds = usa_bounds_frac()
+    n = 40000
+    cfg = _cfg(vax, bounds, n, seed=2025, direct_max=1, pilot_samples=4096)
+    single = ctx.run_bounds(cfg)
+    for world in (2, 3, 8):
+        ctxs = [nat.Context(0) for _ in range(world)]
+        engines = [dist.ContextEngine(c) for c in ctxs]
+        for r, e in enumerate(engines):
+            e.begin(cfg, *dist.shard_range(n, r, world))
+        st = sum(e.param_stats() for e in engines)
+        assert st[3] == n
+        for e in engines:
+            assert not e.set_param_stats(st)
+            e.pilot()
+        outs = [nat.ResultBuffers(cfg.T) for _ in engines]
+        for _ in range(8):
+            for e in engines:
+                e.accumulate()
+            accs = [e.acc_tensor() for e in engines]
+            total = torch.stack(accs).sum(dim=0)
+            for a in accs:
+                a.copy_(total)
+            torch.cuda.synchronize()
+            rcs = [e.finalize(o) for e, o in zip(engines, outs)]
+            assert len(set(rcs)) == 1
+            if rcs[0] != nat.VX_REFINE:
+                break
+        for o in outs:
+            assert _same(single, o)
+            assert o.c.n_rejected == single.c.n_rejected
+            assert o.c.soft_no_mean == pytest.approx(single.c.soft_no_mean, rel=1e-13)
+        for e in engines:
+            e.end()
+        for c in ctxs:
+            c.close()
+
+
+def test_max_running_time_partial_results(vax, ctx):
+    """model.py:187-189, 363-366: a time budget yields partial results plus the error string."""
+    ctx.set_option("chunk_samples", 4096)
+    try:
+        res, err, msg = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95,
+                                      3_000_000, 50000, USA_DATES, max_running_time=1e-4, seed=1,
+                                      direct_max=1, pilot_samples=4096)
+    finally:
+        ctx.set_option("chunk_samples", 1 << 20)
+    k = res["number_finished_samples"]
+    assert 0 < k < 3_000_000
+    assert err == (f"ERROR: Maximum computation time of 0.0001s exceeded. Only {k} of the desired "
+                   f"3000000 Monte Carlo runs were performed.")
+    assert np.isfinite(res[SERIES[0]]["mean"]).all()
+
+
+# ------------------------------------------------------- full BASELINE sizes: properties
+def test_usa_1e6_properties(vax, ctx):
+    """configs[1]: USA scenario at 1e6 samples.  Size-independent properties + the streamed
+    result equals the direct (materialise + exact select) result at full size."""
+    n = 1_000_000
+    res, err, msg = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95, n,
+                                  50000, USA_DATES, seed=12345)
+    assert err == "" and msg == "Agnosticts: 37 - 46%"
+    assert res["number_finished_samples"] == n
+    v, d, r, s = (res[k] for k in SERIES)
+    assert len(v["mean"]) == 564 and len(d["mean"]) == 81
+    assert np.allclose(v["mean"] + s["mean"], r["mean"], rtol=1e-12)   # doses are conserved
+    assert (np.diff(v["mean"]) >= 0).all() and (np.diff(r["mean"]) >= 0).all()
+    for x in (v, d, r, s):
+        assert (x["lower"] <= x["upper"]).all()
+        assert (x["lower"] <= x["mean"] + 1e-9).mean() > 0.95
+    assert 60 < v["mean"][-1] < 85 and v["upper"][-1] <= 88.0 + 1e-9   # pro+agnostics cap
+    direct, _, _ = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95, n,
+                                 50000, USA_DATES, seed=12345, direct_max=2_000_000)
+    for k in SERIES:
+        for f in ("mean", "lower", "upper"):
+            assert np.array_equal(res[k][f], direct[k][f]), (k, f)
+
+
+def test_wide_5y_streamed_properties(vax, ctx):
+    """configs[3] shape (wide bounds, 5-year range) at a size the box finishes in seconds."""
+    b = dict(start_date="2020-12-15", end_date="2025-12-14")
+    res, err, msg = vax.run_model([30, 50], [5.5, 31.5], [0.0, 0.1], [4, 8], [0.9, 1.3], [2.5, 12.5], 99,
+                                  400_000, 50000, b, seed=7)
+    assert err == "" and res["number_finished_samples"] == 400_000
+    v, d, r, s = (res[k] for k in SERIES)
+    assert len(v["mean"]) == 1826 and len(d["mean"]) == 261
+    assert np.allclose(v["mean"] + s["mean"], r["mean"], rtol=1e-12)
+    assert (np.diff(v["mean"]) >= 0).all()
+    assert (v["upper"] <= 94.5 + 1e-9).all()       # 1 - min(anti) = 94.5 %
