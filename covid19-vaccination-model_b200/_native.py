@@ -81,6 +81,7 @@ SYMBOLS = {
     "vx_version": (C.c_char_p, []),
     "vx_device_count": (C.c_int, []),
     "vx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
+    "vx_trim": (C.c_int, [_vp]),
     "vx_run_bounds": (C.c_int, [_vp, _cfgp, _resp]),
     "vx_run_params": (C.c_int, [_vp, _cfgp, _dp, _resp, _i32p]),
     "vx_sample_params": (C.c_int, [_vp, _cfgp, C.c_int64, C.c_int64, _dp, _dp]),
@@ -213,6 +214,9 @@ class Context:
 
     def set_option(self, name: str, value: float):
         self._ck(self._lib.vx_set_option(self._h, name.encode(), float(value)))
+
+    def trim(self):
+        self._ck(self._lib.vx_trim(self._h))
 
     @property
     def launch_count(self) -> int:

@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -84,7 +85,15 @@ struct Job {
 
 } // namespace
 
+enum Slot { SLOT_DUMP = 0, SLOT_ACC, SLOT_WINS, SLOT_TGT, SLOT_RES, SLOT_SEL_RANKS, SLOT_SEL_OUT,
+            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_COUNT };
+
 struct vx_ctx {
+    // grow-only device workspace reused across jobs (cudaMalloc/cudaFree of the pilot matrix
+    // cost more than the pilot itself); released by vx_trim / vx_destroy
+    void *pool[SLOT_COUNT] = {nullptr};
+    size_t pool_cap[SLOT_COUNT] = {0};
+    bool trace = false;
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -126,13 +135,48 @@ int fail(vx_ctx *c, int code, const char *fmt, ...)
         CK(cudaGetLastError());                                                                  \
     } while (0)
 
+int pool_get(vx_ctx *ctx, Slot slot, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 16;
+    if (ctx->pool_cap[slot] < bytes) {
+        if (ctx->pool[slot]) CK(cudaFree(ctx->pool[slot]));
+        ctx->pool[slot] = nullptr;
+        ctx->pool_cap[slot] = 0;
+        const size_t want = bytes + bytes / 8;   // a little headroom: window tables grow per pass
+        cudaError_t e = cudaMalloc(&ctx->pool[slot], want);
+        if (e != cudaSuccess) { cudaGetLastError(); CK(cudaMalloc(&ctx->pool[slot], bytes)); ctx->pool_cap[slot] = bytes; }
+        else ctx->pool_cap[slot] = want;
+    }
+    *out = ctx->pool[slot];
+    return VX_OK;
+}
+
+void pool_release(vx_ctx *ctx)
+{
+    cudaSetDevice(ctx->device);
+    for (int i = 0; i < SLOT_COUNT; ++i) {
+        if (ctx->pool[i]) cudaFree(ctx->pool[i]);
+        ctx->pool[i] = nullptr;
+        ctx->pool_cap[i] = 0;
+    }
+}
+
+struct Phase {   // VX_TRACE=1: host wall time of each phase (after a stream sync) on stderr
+    vx_ctx *c; const char *name; std::chrono::steady_clock::time_point t0;
+    Phase(vx_ctx *c_, const char *n) : c(c_), name(n) { if (c->trace) t0 = std::chrono::steady_clock::now(); }
+    ~Phase() {
+        if (!c->trace) return;
+        cudaStreamSynchronize(c->stream);
+        fprintf(stderr, "[vx trace] %-22s %9.3f ms\n", name,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
+
 void free_job(vx_ctx *ctx)
 {
     Job *j = ctx->job;
     if (!j) return;
     cudaSetDevice(ctx->device);
-    cudaFree(j->d_params); cudaFree(j->d_dump); cudaFree(j->d_exp); cudaFree(j->d_wins);
-    cudaFree(j->d_acc); cudaFree(j->d_tgt); cudaFree(j->d_res);
     if (j->ev0) cudaEventDestroy(j->ev0);
     if (j->ev1) cudaEventDestroy(j->ev1);
     if (j->evA) cudaEventDestroy(j->evA);
@@ -347,18 +391,14 @@ int plan_windows(vx_ctx *ctx, bool from_pilot)
         }
     }
     const int64_t words = ACC_HDR + 3 * R + (int64_t)off;
-    if (words > j->acc_cap) {
-        if (j->d_acc) CK(cudaFree(j->d_acc));
-        j->d_acc = nullptr;
-        CK(cudaMalloc(&j->d_acc, sizeof(unsigned long long) * words));
-        j->acc_cap = words;
-    }
+    { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_ACC, sizeof(unsigned long long) * words, &p_); if (rc_) return rc_; j->d_acc = (unsigned long long *)p_; }
     j->acc_words = words;
     std::vector<Win> hw(R * 2);
     for (int64_t i = 0; i < R * 2; ++i) hw[i] = j->plan[i].w;
-    if (!j->d_wins) CK(cudaMalloc(&j->d_wins, sizeof(Win) * R * 2));
-    if (!j->d_tgt) CK(cudaMalloc(&j->d_tgt, sizeof(long long) * R * 4));
-    if (!j->d_res) CK(cudaMalloc(&j->d_res, sizeof(long long) * R * 4));
+    { void *p_ = nullptr; int rc_;
+      rc_ = pool_get(ctx, SLOT_WINS, sizeof(Win) * R * 2, &p_); if (rc_) return rc_; j->d_wins = (Win *)p_;
+      rc_ = pool_get(ctx, SLOT_TGT, sizeof(long long) * R * 4, &p_); if (rc_) return rc_; j->d_tgt = (long long *)p_;
+      rc_ = pool_get(ctx, SLOT_RES, sizeof(long long) * R * 4, &p_); if (rc_) return rc_; j->d_res = (long long *)p_; }
     CK(cudaMemcpyAsync(j->d_wins, hw.data(), sizeof(Win) * R * 2, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
@@ -372,9 +412,10 @@ int run_select_i32(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld,
     int64_t *d_ranks = nullptr;
     int32_t *d_out = nullptr;
     long long *d_sums = nullptr;
-    CK(cudaMalloc(&d_ranks, sizeof(int64_t) * K));
-    CK(cudaMalloc(&d_out, sizeof(int32_t) * rows * K));
-    CK(cudaMalloc(&d_sums, sizeof(long long) * rows));
+    { void *p_ = nullptr; int rc_;
+      rc_ = pool_get(ctx, SLOT_SEL_RANKS, sizeof(int64_t) * K, &p_); if (rc_) return rc_; d_ranks = (int64_t *)p_;
+      rc_ = pool_get(ctx, SLOT_SEL_OUT, sizeof(int32_t) * rows * K, &p_); if (rc_) return rc_; d_out = (int32_t *)p_;
+      rc_ = pool_get(ctx, SLOT_SEL_SUMS, sizeof(long long) * rows, &p_); if (rc_) return rc_; d_sums = (long long *)p_; }
     CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, ctx->stream));
     vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
     CKL();
@@ -385,7 +426,6 @@ int run_select_i32(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld,
     CK(cudaStreamSynchronize(ctx->stream));
     ord.resize(rows * K);
     for (int64_t i = 0; i < rows * K; ++i) ord[i] = ho[i];
-    cudaFree(d_ranks); cudaFree(d_out); cudaFree(d_sums);
     return VX_OK;
 }
 
@@ -423,7 +463,7 @@ int run_expected(vx_ctx *ctx)
     const int64_t RE = 4 * (int64_t)j->T + j->W;
     if ((double)RE * (double)n * 8.0 > 64e9)
         return fail(ctx, VX_ERR_ARG, "expected-value mode materialises fp64 trajectories: n_samples too large");
-    CK(cudaMalloc(&j->d_exp, sizeof(double) * RE * n));
+    { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_EXP, sizeof(double) * RE * n, &p_); if (rc_) return rc_; j->d_exp = (double *)p_; }
     SimArgs a = make_args(j, 0, n, j->d_params);
     vx_expected_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, j->d_exp, n);
     CKL();
@@ -484,6 +524,7 @@ int vx_create(vx_ctx **out, int device)
     if (device < 0 || device >= n) return fail(nullptr, VX_ERR_ARG, "device %d not in [0,%d)", device, n);
     vx_ctx *c = new vx_ctx();
     c->device = device;
+    c->trace = getenv("VX_TRACE") != nullptr;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
@@ -503,7 +544,7 @@ void vx_destroy(vx_ctx *ctx)
 {
     if (!ctx) return;
     free_job(ctx);
-    cudaSetDevice(ctx->device);
+    pool_release(ctx);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -511,6 +552,14 @@ void vx_destroy(vx_ctx *ctx)
 const char *vx_last_error(vx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t vx_launch_count(vx_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int vx_trim(vx_ctx *ctx)
+{
+    if (!ctx) return VX_ERR_ARG;
+    if (ctx->job) return fail(ctx, VX_ERR_STATE, "vx_trim while a job is open");
+    pool_release(ctx);
+    return VX_OK;
+}
 
 int vx_set_option(vx_ctx *ctx, const char *name, double value)
 {
@@ -587,7 +636,7 @@ static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_fir
     if (h_params) {
         nvmax_hi = 0;
         for (int64_t i = 0; i < cfg->n_samples; ++i) nvmax_hi = std::max(nvmax_hi, h_params[6 * i + 5]);
-        CK(cudaMalloc(&j->d_params, sizeof(double) * 6 * cfg->n_samples));
+        { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_PARAMS, sizeof(double) * 6 * cfg->n_samples, &p_); if (rc_) return rc_; j->d_params = (double *)p_; }
         CK(cudaMemcpyAsync(j->d_params, h_params, sizeof(double) * 6 * cfg->n_samples, cudaMemcpyHostToDevice, ctx->stream));
         j->gstats[3] = (double)cfg->n_samples;
         j->stats_set = true;
@@ -613,6 +662,7 @@ int vx_job_param_stats(vx_ctx *ctx, double stats[4])
     Job *j = ctx->job;
     int rc = need_device(ctx);
     if (rc) return rc;
+    Phase ph_(ctx, "param_stats");
     stats[0] = stats[1] = stats[2] = 0.0;
     stats[3] = (double)j->shard_count;
     if (j->explicit_params || j->shard_count == 0) return VX_OK;
@@ -625,9 +675,9 @@ int vx_job_param_stats(vx_ctx *ctx, double stats[4])
     const int64_t n = j->shard_count, grid = (n + 255) / 256;
     unsigned long long *d_stop = nullptr;
     double *d_part = nullptr, *d_out = nullptr;
-    CK(cudaMalloc(&d_stop, 16));
-    CK(cudaMalloc(&d_part, sizeof(double) * 3 * grid));
-    CK(cudaMalloc(&d_out, sizeof(double) * 3));
+    { void *p_ = nullptr; int rc_;
+      rc_ = pool_get(ctx, SLOT_STATS_PART, sizeof(double) * 3 * grid, &p_); if (rc_) return rc_; d_part = (double *)p_;
+      rc_ = pool_get(ctx, SLOT_STATS_MISC, 64, &p_); if (rc_) return rc_; d_stop = (unsigned long long *)p_; d_out = (double *)p_ + 4; }
     const unsigned long long hstop[2] = {0ull, (unsigned long long)(10 * j->cfg.n_samples)};
     CK(cudaMemcpyAsync(d_stop, hstop, 16, cudaMemcpyHostToDevice, ctx->stream));
     Bounds bd;
@@ -638,7 +688,6 @@ int vx_job_param_stats(vx_ctx *ctx, double stats[4])
     CKL();
     CK(cudaMemcpyAsync(stats, d_out, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_stop); cudaFree(d_part); cudaFree(d_out);
     return VX_OK;
 }
 
@@ -674,6 +723,7 @@ int vx_job_pilot(vx_ctx *ctx)
             if (cudaEventElapsedTime(&ms, j->evA, j->evB) == cudaSuccess) j->pilot_ms += ms;
         }
     } pilot_timer(ctx, j);
+    Phase ph_(ctx, "pilot (total)");
     if (j->cfg.mode == VX_MODE_EXPECTED) return run_expected(ctx);
 
     const int64_t n = j->cfg.n_samples, R = j->R;
@@ -690,8 +740,8 @@ int vx_job_pilot(vx_ctx *ctx)
     const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(n));
     j->n_pilot = np;
     if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
-    CK(cudaMalloc(&j->d_dump, sizeof(int32_t) * R * np));
-    rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np);
+    { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * R * np, &p_); if (rc_) return rc_; j->d_dump = (int32_t *)p_; }
+    { Phase ph2_(ctx, "  pilot stepper"); rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np); }
     if (rc) return rc;
 
     std::vector<int64_t> ranks(4), ord;
@@ -717,7 +767,7 @@ int vx_job_pilot(vx_ctx *ctx)
         ranks[2 * q] = (int64_t)std::min(std::max(ra, 0.0), (double)(np - 1));
         ranks[2 * q + 1] = (int64_t)std::min(std::max(rb, 0.0), (double)(np - 1));
     }
-    rc = run_select_i32(ctx, j->d_dump, R, np, np, ranks, ord, sums);
+    { Phase ph2_(ctx, "  pilot select"); rc = run_select_i32(ctx, j->d_dump, R, np, np, ranks, ord, sums); }
     if (rc) return rc;
     j->pilot_stats = ord;
     // a bracket that ran off either end of the pilot sample is open on that side
@@ -726,8 +776,8 @@ int vx_job_pilot(vx_ctx *ctx)
             if (ranks[2 * q] == 0) j->pilot_stats[r * 4 + 2 * q] = 0;
             if (ranks[2 * q + 1] == np - 1) j->pilot_stats[r * 4 + 2 * q + 1] = j->vmax[series_of_row(j, r)];
         }
-    CK(cudaFree(j->d_dump));
     j->d_dump = nullptr;
+    Phase ph3_(ctx, "  plan windows");
     return plan_windows(ctx, true);
 }
 
@@ -748,6 +798,7 @@ int vx_job_accumulate(vx_ctx *ctx)
     if (j->direct || j->finished) return VX_OK;
     int rc = need_device(ctx);
     if (rc) return rc;
+    Phase ph_(ctx, "accumulate (fold)");
     CK(cudaMemsetAsync(j->d_acc, 0, sizeof(unsigned long long) * j->acc_words, ctx->stream));
     const bool first_pass = j->n_passes == 0;
     const int64_t todo = first_pass ? j->shard_count : j->shard_done;
@@ -789,6 +840,7 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     int rc = need_device(ctx);
     if (rc) return rc;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_finalize");
+    Phase ph_(ctx, "finalize");
     if (!j->finished) {
         const int64_t R = j->R;
         unsigned long long hdr[ACC_HDR];

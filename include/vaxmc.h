@@ -107,6 +107,9 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * "use_pilot" (0: start from the coarse full-range windows), "chunk_samples"
  * (granularity of the max_running_time check, default 2^20).                          */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
+/* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
+ * vx_trim returns it to the driver. */
+int vx_trim(vx_ctx *ctx);
 
 /* ---- whole job on one GPU (run_sampling, model.py:139-228, + parameter draw 231-303) */
 int vx_run_bounds(vx_ctx *ctx, const vx_config *cfg, vx_result *res);
