@@ -36,13 +36,9 @@ enum : uint32_t {
 __host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
                                                       uint32_t &c3, uint32_t k0, uint32_t k1)
 {
-#ifdef __CUDA_ARCH__
-    const uint32_t hi0 = __umulhi(PHILOX_M0, c0), hi1 = __umulhi(PHILOX_M1, c2);
-#else
-    const uint32_t hi0 = (uint32_t)(((uint64_t)PHILOX_M0 * c0) >> 32);
-    const uint32_t hi1 = (uint32_t)(((uint64_t)PHILOX_M1 * c2) >> 32);
-#endif
-    const uint32_t lo0 = PHILOX_M0 * c0, lo1 = PHILOX_M1 * c2;
+    const uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), hi1 = (uint32_t)(p1 >> 32);
+    const uint32_t lo0 = (uint32_t)p0, lo1 = (uint32_t)p1;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
 }
@@ -90,29 +86,45 @@ __constant__ float c_rcp[72];
 
 // Poisson(lam) variate.
 //   lam == 0          -> 0 (numpy returns 0 without consuming the stream, model.py:104,116)
-//   0 < lam < 10      -> exact inversion by sequential search with one uniform (word w)
-//   lam >= 10         -> floor of the continuous inverse Q(z) of the Poisson CDF expanded
-//                        to O(1/lam) around the normal quantile z (Cornish-Fisher with the
-//                        lattice correction; Giles, ACM TOMS 42(1), 2016, eq. for Q_N1):
+//   0 < lam < 4       -> exact inversion by sequential search with one uniform (word w)
+//   lam >= 4          -> floor of the continuous inverse Q(z) of the Poisson CDF expanded
+//                        around the normal quantile z (Cornish-Fisher with the lattice
+//                        correction; the first three orders are Giles' Q_N1, ACM TOMS 42(1),
+//                        2016):
 //                          Q = lam + s z + (1/3 + z^2/6) + (-z/36 - z^3/72)/s
-//                              + (-8/405 + 7 z^2/810 + z^4/270)/lam,        s = sqrt(lam)
-//                        sup-CDF error vs the exact law <= 5.1e-5 at lam=10, 1.6e-5 at 16,
-//                        <1e-5 above 32 (tests/test_sampler_math.py computes these).
+//                              + (-8/405 + 7 z^2/810 + z^4/270)/lam
+//                              + (a1 z + a3 z^3 + a5 z^5)/lam^1.5
+//                              + (b0 + b2 z^2 + b4 z^4 + b6 z^6)/lam^2,      s = sqrt(lam)
+//                        The two highest orders are a weighted least-squares fit of the exact
+//                        jump points Phi^-1(F(k)) -> k+1 over lam in [4,32] (their asymptotic
+//                        values are a=(.01725,-.00352,-.00133), b=(-.0015,-.0113,.0013,.0006));
+//                        oracle/fit_poisson_cf.py regenerates them and prints the resulting
+//                        sup-CDF error against the exact law: 6.6e-5 at lam=4, <=1.8e-5 for
+//                        lam>=5, <5e-6 for lam>=16 (tests/test_sampler_math.py pins these).
+constexpr float POISSON_INV_MAX = 4.0f;
+constexpr float CF_A1 = 0.01534796f, CF_A3 = 0.00120633f, CF_A5 = -0.00210642f;
+constexpr float CF_B0 = 0.00125185f, CF_B2 = -0.01826666f, CF_B4 = 0.00198713f, CF_B6 = 0.00056336f;
+
 __device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
 {
-    const float rs = fast_rsqrt(lam), s = lam * rs, z2 = z * z;
+    const float rs = fast_rsqrt(lam), s = lam * rs, z2 = z * z, rl = rs * rs;
+    // the two fitted orders only matter for small lam; evaluate them at |z| <= 5 so that the
+    // odd/even degree-5/6 polynomials cannot bend Q back in the far tails
+    const float zc = fminf(fmaxf(z, -5.0f), 5.0f), zc2 = zc * zc;
     float q = fmaf(s, z, fmaf(z2, 0.16666667f, 0.33333334f));
     q = fmaf(rs * z, fmaf(z2, -0.013888889f, -0.027777778f), q);
-    q = fmaf(rs * rs, fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f), q);
+    q = fmaf(rl, fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f), q);
+    q = fmaf(rl * rs * zc, fmaf(zc2, fmaf(zc2, CF_A5, CF_A3), CF_A1), q);
+    q = fmaf(rl * rl, fmaf(zc2, fmaf(zc2, fmaf(zc2, CF_B6, CF_B4), CF_B2), CF_B0), q);
     const float lf = floorf(lam);
     int x = (int)lf + (int)floorf((lam - lf) + q);
     x = max(x, 0);
-    if (lam < 10.0f) {
+    if (lam < POISSON_INV_MAX) {
         x = 0;
         if (lam > 0.0f) {
             const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
             float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
-            while (u >= cdf && x < 64) {
+            while (u >= cdf && x < 40) {
                 ++x;
                 p *= lam * c_rcp[x];
                 cdf += p;
@@ -371,14 +383,11 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) vx_sim_kernel(const SimArgs a)
                 uint32_t sum = 0, clo = 0, chi = 0;
                 uint32_t rb_lo = 0xffffffffu, rc_lo = 0, rb_hi = 0xffffffffu, rc_hi = 0;
                 const int *row = tile + lane * TILE_LD;
-#pragma unroll 4
-                for (int s = 0; s < nvalid; ++s) {
-                    const int v = row[s];
-                    sum += (uint32_t)v;
+                // in-window values are rare (the windows hold ~1% of the mass): one combined
+                // test per 4 samples, run-length aggregated histogram updates on the slow path
+                auto slow = [&](int v) {
                     const int dl = v - wl.a, dh = v - wh.a;
-                    clo += (uint32_t)dl >> 31;
-                    chi += (uint32_t)dh >> 31;
-                    if ((uint32_t)dl < wl.len) {            // rare: run-length aggregated
+                    if ((uint32_t)dl < wl.len) {
                         const uint32_t b = (uint32_t)dl >> wl.shift;
                         if (b != rb_lo) {
                             if (rc_lo) atomicAdd(hist + wl.off + rb_lo, (unsigned long long)rc_lo);
@@ -394,6 +403,25 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) vx_sim_kernel(const SimArgs a)
                         }
                         ++rc_hi;
                     }
+                };
+                int s = 0;
+#pragma unroll 1
+                for (; s + 4 <= nvalid; s += 4) {
+                    const int v0 = row[s], v1 = row[s + 1], v2 = row[s + 2], v3 = row[s + 3];
+                    sum += (uint32_t)v0 + (uint32_t)v1 + (uint32_t)v2 + (uint32_t)v3;
+                    const uint32_t l0 = v0 - wl.a, l1 = v1 - wl.a, l2 = v2 - wl.a, l3 = v3 - wl.a;
+                    const uint32_t h0 = v0 - wh.a, h1 = v1 - wh.a, h2 = v2 - wh.a, h3 = v3 - wh.a;
+                    clo += (l0 >> 31) + (l1 >> 31) + (l2 >> 31) + (l3 >> 31);
+                    chi += (h0 >> 31) + (h1 >> 31) + (h2 >> 31) + (h3 >> 31);
+                    const uint32_t ml = min(min(l0, l1), min(l2, l3)), mh = min(min(h0, h1), min(h2, h3));
+                    if (ml < wl.len || mh < wh.len) { slow(v0); slow(v1); slow(v2); slow(v3); }
+                }
+                for (; s < nvalid; ++s) {
+                    const int v = row[s];
+                    sum += (uint32_t)v;
+                    clo += (uint32_t)(v - wl.a) >> 31;
+                    chi += (uint32_t)(v - wh.a) >> 31;
+                    slow(v);
                 }
                 if (rc_lo) atomicAdd(hist + wl.off + rb_lo, (unsigned long long)rc_lo);
                 if (rc_hi) atomicAdd(hist + wh.off + rb_hi, (unsigned long long)rc_hi);

@@ -1,0 +1,62 @@
+"""CPU: the mathematics behind the device RNG/sampler (no GPU needed).
+
+* Philox4x32-10 restatement against the Random123 known-answer vectors, and the counter layout.
+* The Poisson sampler's normal-quantile expansion (constants parsed out of the CUDA source)
+  against the exact Poisson law: sup-CDF error bounds quoted in DESIGN.md.
+"""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import philox_ref as pr
+from fit_poisson_cf import law_error, q5
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUH = os.path.join(ROOT, "covid19-vaccination-model_b200", "csrc", "vaxmc_kernels.cuh")
+
+
+def _const(name):
+    src = open(CUH).read()
+    m = re.search(rf"\b{name}\s*=\s*(-?[0-9.eE+-]+)f", src)
+    assert m, name
+    return float(m.group(1))
+
+
+def test_philox_known_answers():
+    for c, k, e in pr.KAT:
+        r = pr.philox4x32_10(*[np.uint32(x) for x in c], k[0], k[1])
+        assert [int(x) for x in r] == list(e)
+
+
+def test_parameter_draw_restatement_properties():
+    b = [0.5, 0.9, 0.3, 0.6, 0.0, 0.1, 3, 4, 0.002, 0.0024, 0.1, 0.1]
+    p, s, rej = pr.draw_params(b, 99, 0, 4000)
+    assert (p[:, 0] + p[:, 1] <= 1.0).all() and rej.sum() > 0
+    assert ((p[:, 0] >= 0.5) & (p[:, 0] <= 0.9) & (p[:, 1] >= 0.3) & (p[:, 1] <= 0.6)).all()
+    assert (p[:, 5] == 0.1).all()                         # single-value bound -> constant
+    # a sample's tuple depends only on (seed, global id): sharding cannot change it
+    p2, _, _ = pr.draw_params(b, 99, 1000, 500)
+    assert np.array_equal(p2, p[1000:1500])
+    p3, _, _ = pr.draw_params(b, 100, 0, 100)
+    assert not np.array_equal(p3, p[:100])
+
+
+def test_poisson_expansion_error_bounds():
+    a = [_const("CF_A1"), _const("CF_A3"), _const("CF_A5")]
+    b = [_const("CF_B0"), _const("CF_B2"), _const("CF_B4"), _const("CF_B6")]
+    thr = _const("POISSON_INV_MAX")
+    assert thr == 4.0
+    bounds = {4: 8e-5, 5: 3e-5, 6: 3e-5, 8: 2e-5, 10: 2e-5, 16: 8e-6, 32: 5e-6, 100: 5e-6, 2857: 5e-6}  # >=32: grid resolution of the check
+    for lam, bound in bounds.items():
+        sup, chi = law_error(lam, lambda z, l: q5(z, l, a, b), M=1_000_001)
+        assert sup <= bound, (lam, sup)
+        assert chi <= 5e-7 or lam > 1000, (lam, chi)        # needs > 3e7 draws at ONE lam to show at 3 sigma
+
+
+def test_inversion_regime_tail_is_negligible():
+    # the sequential search is capped at 40 steps; for lam < 4 that tail is < 1e-25
+    from scipy import stats
+
+    assert stats.poisson.sf(40, 4.0) < 1e-25
