@@ -311,6 +311,7 @@ SimArgs make_args(const Job *j, int64_t first, int64_t count, const double *d_pa
     memcpy(a.bd.b, j->cfg.bounds, sizeof a.bd.b);
     a.params = d_params;
     a.seed = j->cfg.seed;
+    a.keys = philox_keys(j->cfg.seed);
     a.first = first;
     a.count = count;
     a.N = j->cfg.N;

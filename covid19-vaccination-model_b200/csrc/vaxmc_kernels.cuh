@@ -33,12 +33,24 @@ enum : uint32_t {
     TAG_TEST = 7
 };
 
+__host__ __device__ __forceinline__ void mulhilo32(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi)
+{
+#ifdef __CUDA_ARCH__
+    // one IMAD.WIDE.U32 instead of IMAD.HI + IMAD
+    asm("{\n\t.reg .b64 p;\n\tmul.wide.u32 p, %2, %3;\n\tmov.b64 {%0,%1}, p;\n\t}"
+        : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+#else
+    const uint64_t p = (uint64_t)a * b;
+    lo = (uint32_t)p; hi = (uint32_t)(p >> 32);
+#endif
+}
+
 __host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
                                                       uint32_t &c3, uint32_t k0, uint32_t k1)
 {
-    const uint64_t p0 = (uint64_t)PHILOX_M0 * c0, p1 = (uint64_t)PHILOX_M1 * c2;
-    const uint32_t hi0 = (uint32_t)(p0 >> 32), hi1 = (uint32_t)(p1 >> 32);
-    const uint32_t lo0 = (uint32_t)p0, lo1 = (uint32_t)p1;
+    uint32_t hi0, lo0, hi1, lo1;
+    mulhilo32(PHILOX_M0, c0, lo0, hi0);
+    mulhilo32(PHILOX_M1, c2, lo1, hi1);
     const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
     c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
 }
@@ -51,6 +63,26 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
         philox_round(c0, c1, c2, c3, k0, k1);
         k0 += PHILOX_W0; k1 += PHILOX_W1;
     }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Round keys precomputed on the host (key + r*W): in the stepper they are kernel-parameter
+// constants, so each round is 2 IMAD.WIDE + 2 LOP3 with a constant-bank operand.
+struct PhiloxKeys { uint32_t k[20]; };
+
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed)
+{
+    PhiloxKeys K;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { K.k[2 * r] = k0; K.k[2 * r + 1] = k1; k0 += PHILOX_W0; k1 += PHILOX_W1; }
+    return K;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKeys &K)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) philox_round(c0, c1, c2, c3, K.k[2 * r], K.k[2 * r + 1]);
     return make_uint4(c0, c1, c2, c3);
 }
 
@@ -75,7 +107,7 @@ __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, float &z0,
 {
     const float u1 = fmaf((float)w0, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
     // -2 ln(u1) = (-2 ln 2) * lg2(u1)
-    const float rad = fast_sqrt(fmaxf(-1.3862943611198906f * fast_lg2(u1), 0.0f));
+    const float rad = fast_sqrt(-1.3862943611198906f * fast_lg2(u1));   // u1 <= 1: argument >= +-0
     const float ang = (float)(int32_t)w1 * 1.4629180792671596e-09f; // pi * 2^-31
     z0 = rad * fast_cos(ang);
     z1 = rad * fast_sin(ang);
@@ -111,14 +143,14 @@ __device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
     // the two fitted orders only matter for small lam; evaluate them at |z| <= 5 so that the
     // odd/even degree-5/6 polynomials cannot bend Q back in the far tails
     const float zc = fminf(fmaxf(z, -5.0f), 5.0f), zc2 = zc * zc;
-    float q = fmaf(s, z, fmaf(z2, 0.16666667f, 0.33333334f));
+    float q = fmaf(s, z, fmaf(z2, 0.16666667f, 0.33333334f));   // + lam added last
     q = fmaf(rs * z, fmaf(z2, -0.013888889f, -0.027777778f), q);
     q = fmaf(rl, fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f), q);
     q = fmaf(rl * rs * zc, fmaf(zc2, fmaf(zc2, CF_A5, CF_A3), CF_A1), q);
     q = fmaf(rl * rl, fmaf(zc2, fmaf(zc2, fmaf(zc2, CF_B6, CF_B4), CF_B2), CF_B0), q);
-    const float lf = floorf(lam);
-    int x = (int)lf + (int)floorf((lam - lf) + q);
-    x = max(x, 0);
+    // lam + q in fp32: at lam = 1e5 one ulp is 0.008, i.e. a 1e-5 shift of the CDF -- below the
+    // expansion's own error; rounding to nearest keeps it unbiased
+    int x = max(__float2int_rd(lam + q), 0);
     if (lam < POISSON_INV_MAX) {
         x = 0;
         if (lam > 0.0f) {
@@ -257,6 +289,7 @@ struct SimArgs {
     Bounds bd;
     const double *params;   // explicit tuples [count][6] (then bd is unused) or nullptr
     uint64_t seed;
+    PhiloxKeys keys;        // philox_keys(seed)
     int64_t first;          // GLOBAL id of local sample 0 (Philox counter)
     int64_t count;          // samples in this launch
     int64_t N;
@@ -334,7 +367,7 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) vx_sim_kernel(const SimArgs a)
 #pragma unroll 1
             for (int dd = 0; dd < dend; ++dd) {
                 const int day = dw + dd;
-                const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)day, TAG_DAY, k0, k1);
+                const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)day, TAG_DAY, a.keys);
                 float z1, z2;
                 normal_pair(r.x, r.y, z1, z2);
                 // ---- vaccination draw, model.py:102-112
