@@ -451,8 +451,8 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
 
 int64_t default_pilot(int64_t n)
 {
-    int64_t p = 65536;
-    while (p < n / 16 && p < ((int64_t)1 << 20)) p <<= 1;
+    int64_t p = 32768;
+    while (p < n / 32 && p < ((int64_t)1 << 20)) p <<= 1;
     return p;
 }
 
@@ -777,7 +777,6 @@ int vx_job_pilot(vx_ctx *ctx)
             if (ranks[2 * q] == 0) j->pilot_stats[r * 4 + 2 * q] = 0;
             if (ranks[2 * q + 1] == np - 1) j->pilot_stats[r * 4 + 2 * q + 1] = j->vmax[series_of_row(j, r)];
         }
-    j->d_dump = nullptr;
     Phase ph3_(ctx, "  plan windows");
     return plan_windows(ctx, true);
 }
@@ -805,8 +804,16 @@ int vx_job_accumulate(vx_ctx *ctx)
     const int64_t todo = first_pass ? j->shard_count : j->shard_done;
     const bool timed = first_pass && j->cfg.max_running_time > 0.0;
     const int64_t chunk = timed ? ctx->chunk_samples : ((int64_t)1 << 30);
-    int64_t done = 0;
     CK(cudaEventRecord(j->evA, ctx->stream));
+    // samples of this shard that the pilot already simulated: fold its matrix, not a re-run
+    const int64_t lo = j->shard_first, hi = j->shard_first + todo;
+    const int64_t pil_hi = (j->d_dump && j->n_pilot > 0) ? std::min(hi, j->n_pilot) : lo;
+    int64_t done = 0;
+    if (pil_hi > lo) {
+        vx_fold_matrix_kernel<<<(unsigned)j->R, 256, 0, ctx->stream>>>(j->d_dump, j->n_pilot, lo, pil_hi, j->d_wins, j->d_acc, (int)j->R);
+        CKL();
+        done = pil_hi - lo;
+    }
     while (done < todo) {
         const int64_t cnt = std::min(chunk, todo - done);
         SimArgs a = make_args(j, j->shard_first + done, cnt,

@@ -303,12 +303,12 @@ struct SimArgs {
 constexpr int ACC_HDR = 8;
 constexpr int WIN_DAYS = 14;       // one warp tile = 2 weeks = 14+14+2+2 = 32 rows
 constexpr int TILE_LD = 33;        // padded leading dimension: conflict-free both ways
-constexpr int SIM_THREADS = 256;
+constexpr int SIM_THREADS = 128;       // warps are independent: small CTAs = short tail
 
 enum { SIM_DUMP = 0, SIM_FOLD = 1 };
 
 template <int MODE>
-__global__ void __launch_bounds__(SIM_THREADS, 4) vx_sim_kernel(const SimArgs a)
+__global__ void __launch_bounds__(SIM_THREADS, 8) vx_sim_kernel(const SimArgs a)
 {
     __shared__ int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -467,6 +467,43 @@ __global__ void __launch_bounds__(SIM_THREADS, 4) vx_sim_kernel(const SimArgs a)
     }
     if (MODE == SIM_FOLD && lane == 0)
         atomicAdd(a.acc + 0, (unsigned long long)nvalid);  // header word 0: samples folded
+}
+
+// Fold of an already materialised block of raw rows (the pilot matrix) into the accumulator
+// slab: same sums / counts-below / window histograms as the FOLD stepper produces, so the
+// pilot samples are not simulated twice.  One CTA per row, columns [c0, c1).
+__global__ void __launch_bounds__(256) vx_fold_matrix_kernel(const int32_t *__restrict__ dump,
+                                                             int64_t ld, int64_t c0, int64_t c1,
+                                                             const Win *__restrict__ wins,
+                                                             unsigned long long *acc, int R)
+{
+    __shared__ unsigned long long sh[3][256];
+    const int row = blockIdx.x;
+    const Win wl = wins[row * 2], wh = wins[row * 2 + 1];
+    unsigned long long *hist = acc + ACC_HDR + 3 * (int64_t)R;
+    const int32_t *src = dump + (int64_t)row * ld;
+    unsigned long long sum = 0, clo = 0, chi = 0;
+    for (int64_t c = c0 + threadIdx.x; c < c1; c += 256) {
+        const int v = src[c];
+        sum += (unsigned long long)(uint32_t)v;
+        const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
+        clo += dl >> 31; chi += dh >> 31;
+        if (dl < wl.len) atomicAdd(hist + wl.off + (dl >> wl.shift), 1ull);
+        if (dh < wh.len) atomicAdd(hist + wh.off + (dh >> wh.shift), 1ull);
+    }
+    sh[0][threadIdx.x] = sum; sh[1][threadIdx.x] = clo; sh[2][threadIdx.x] = chi;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off)
+            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(acc + ACC_HDR + row, sh[0][0]);
+        if (sh[1][0]) atomicAdd(acc + ACC_HDR + R + 2 * row, sh[1][0]);
+        if (sh[2][0]) atomicAdd(acc + ACC_HDR + R + 2 * row + 1, sh[2][0]);
+        if (row == 0) atomicAdd(acc + 0, (unsigned long long)(c1 - c0));
+    }
 }
 
 // Expected-value stepper: np.random.poisson := identity, state carried in fp64 exactly as

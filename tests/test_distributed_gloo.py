@@ -1,0 +1,174 @@
+"""CPU, world_size=2 over gloo: the multi-rank driver (covid19-vaccination-model_b200/distributed.py).
+
+The arithmetic of a rank lives in libvaxmc.so and needs a GPU; here a FakeEngine with the
+same interface folds a deterministic integer function of the GLOBAL sample id, which is
+enough to pin what the driver is responsible for: disjoint contiguous shards that cover the
+range, the float64 all-reduce of the parameter statistics, the int64 all-reduce of the
+accumulator slab once per pass, the VX_REFINE loop, the abort path -- and that the merged
+integers do not depend on the number of ranks.
+"""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "covid19-vaccination-model_b200"
+
+
+class _C:
+    aborted = 0
+    n_rejected = 0
+    n_finished = 0
+
+
+class _Out:
+    def __init__(self):
+        self.c = _C()
+        self.merged = None
+
+
+class FakeEngine:
+    """Integer fold of f(id) = (id * 2654435761) % 1009 over the shard, two passes."""
+
+    def __init__(self, infeasible=False):
+        self.infeasible = infeasible
+        self.passes = 0
+        self.calls = []
+
+    def begin(self, cfg, first, count):
+        self.first, self.count, self.n = first, count, cfg.n_samples
+        self.calls.append(("begin", first, count))
+
+    def param_stats(self):
+        ids = np.arange(self.first, self.first + self.count, dtype=np.int64)
+        rej = float((ids % 3 == 0).sum()) if not self.infeasible else 11.0 * self.count
+        s = (ids % 100) / 100.0
+        return np.array([rej, s.sum(), (s * s).sum(), float(self.count)])
+
+    def stats_tensor(self, st):
+        return torch.from_numpy(np.ascontiguousarray(st))
+
+    def set_param_stats(self, st):
+        self.gstats = np.array(st)
+        return st[0] > 10.0 * self.n
+
+    def pilot(self):
+        self.calls.append(("pilot",))
+
+    def accumulate(self):
+        ids = np.arange(self.first, self.first + self.count, dtype=np.uint64)
+        f = (ids * np.uint64(2654435761)) % np.uint64(1009)
+        hist = np.bincount(f.astype(np.int64), minlength=1009)
+        self.acc = torch.from_numpy(np.concatenate([[self.count, int(f.sum())], hist]).astype(np.int64))
+        self.passes += 1
+
+    def acc_tensor(self):
+        return self.acc
+
+    def finalize(self, out):
+        out.merged = self.acc.clone().numpy()
+        out.c.n_finished = int(out.merged[0])
+        return 1 if self.passes < 2 else 0          # VX_REFINE once, then VX_OK
+
+    def end(self):
+        self.calls.append(("end",))
+
+
+class _Cfg:
+    def __init__(self, n):
+        self.n_samples = n
+        self.T = 10
+
+
+def _worker(rank, world, port, n, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        d = importlib.import_module(PKG + ".distributed")
+        eng = FakeEngine()
+        n_reduces = [0]
+
+        def all_reduce(t):
+            n_reduces[0] += 1
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+        out = d.run_sharded(eng, _Cfg(n), rank, world, all_reduce, _Out)
+        bad = FakeEngine(infeasible=True)
+        out_bad = d.run_sharded(bad, _Cfg(n), rank, world, all_reduce, _Out)
+        q.put((rank, out.merged.tolist(), eng.gstats.tolist(), eng.passes, n_reduces[0], eng.calls,
+               out_bad.c.aborted, bad.passes))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _expected(n):
+    ids = np.arange(n, dtype=np.uint64)
+    f = (ids * np.uint64(2654435761)) % np.uint64(1009)
+    hist = np.bincount(f.astype(np.int64), minlength=1009)
+    merged = np.concatenate([[n, int(f.sum())], hist]).astype(np.int64)
+    idl = np.arange(n)
+    s = (idl % 100) / 100.0
+    return merged, np.array([float((idl % 3 == 0).sum()), s.sum(), (s * s).sum(), float(n)])
+
+
+@pytest.mark.parametrize("n", [1001, 64])
+def test_two_rank_gloo_merge_equals_single_rank(n):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    merged, stats = _expected(n)
+    for rank, m, st, passes, n_red, calls, aborted, bad_passes in res:
+        assert np.array_equal(np.array(m), merged)              # integer merge is exact
+        assert np.allclose(st, stats, rtol=1e-14)
+        assert passes == 2                                       # one VX_REFINE round trip
+        assert n_red == 1 + 2 + 1                                # stats + one per pass (+ abort job's stats)
+        assert calls[0][0] == "begin" and calls[1] == ("pilot",) and calls[-1] == ("end",)
+        assert aborted == 1 and bad_passes == 0                  # abort path: no pass is run
+
+
+def test_shard_range_partitions_exactly():
+    d = importlib.import_module(PKG + ".distributed")
+    for n in (0, 1, 7, 8, 9, 1000, 10**9 + 7):
+        for world in (1, 2, 3, 4, 8):
+            parts = [d.shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0
+            for (f0, c0), (f1, c1) in zip(parts, parts[1:]):
+                assert f0 + c0 == f1
+            assert parts[-1][0] + parts[-1][1] == n
+            counts = [c for _, c in parts]
+            assert max(counts) - min(counts) <= 1
+
+
+def test_single_process_driver_equals_sharded_sum():
+    """Same fake engine, world=1: the merged slab must equal the 2-rank result (no collective)."""
+    d = importlib.import_module(PKG + ".distributed")
+    eng = FakeEngine()
+    out = d.run_sharded(eng, _Cfg(1001), 0, 1, lambda t: None, _Out)
+    merged, _ = _expected(1001)
+    assert np.array_equal(out.merged, merged)
