@@ -86,7 +86,7 @@ struct Job {
 } // namespace
 
 enum Slot { SLOT_DUMP = 0, SLOT_ACC, SLOT_WINS, SLOT_TGT, SLOT_RES, SLOT_SEL_RANKS, SLOT_SEL_OUT,
-            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_COUNT };
+            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_PERM, SLOT_SORT, SLOT_COUNT };
 
 struct vx_ctx {
     // grow-only device workspace reused across jobs (cudaMalloc/cudaFree of the pilot matrix
@@ -104,6 +104,7 @@ struct vx_ctx {
     int64_t chunk_samples = 1 << 20;
     double pilot_sigmas = 6.0;
     int64_t use_pilot = 1;
+    int64_t sort_samples = 1;
     int sm_count = 148;
 };
 
@@ -570,6 +571,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "chunk_samples") { if (value < 256) return fail(ctx, VX_ERR_ARG, "chunk_samples too small"); ctx->chunk_samples = (int64_t)value; }
     else if (s == "pilot_sigmas") { if (!(value >= 0)) return fail(ctx, VX_ERR_ARG, "pilot_sigmas < 0"); ctx->pilot_sigmas = value; }
     else if (s == "use_pilot") ctx->use_pilot = value != 0;
+    else if (s == "sort_samples") ctx->sort_samples = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }
@@ -820,6 +822,23 @@ int vx_job_accumulate(vx_ctx *ctx)
                               j->d_params ? j->d_params + 6 * (j->shard_first + done) : nullptr);
         a.wins = j->d_wins;
         a.acc = j->d_acc;
+        if (ctx->sort_samples && !j->explicit_params && cnt >= 4096) {
+            // counting sort of the chunk by pressure bucket -> lanes of a warp share a regime
+            void *p_ = nullptr;
+            rc = pool_get(ctx, SLOT_PERM, sizeof(int32_t) * cnt, &p_); if (rc) return rc;
+            int32_t *d_perm = (int32_t *)p_;
+            rc = pool_get(ctx, SLOT_SORT, sizeof(uint32_t) * SORT_BUCKETS, &p_); if (rc) return rc;
+            uint32_t *d_cnt = (uint32_t *)p_;
+            const unsigned sgrid = (unsigned)((cnt + 255) / 256);
+            CK(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * SORT_BUCKETS, ctx->stream));
+            vx_bucket_count_kernel<<<sgrid, 256, 0, ctx->stream>>>(j->cfg.seed, a.first, cnt, d_cnt);
+            CKL();
+            vx_bucket_scan_kernel<<<1, SORT_BUCKETS, 0, ctx->stream>>>(d_cnt);
+            CKL();
+            vx_bucket_scatter_kernel<<<sgrid, 256, 0, ctx->stream>>>(j->cfg.seed, a.first, cnt, d_cnt, d_perm);
+            CKL();
+            a.perm = d_perm;
+        }
         const int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
         vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
         CKL();

@@ -104,7 +104,8 @@ const char *vx_version(void);
 int vx_device_count(void);              /* 0 when no CUDA device is usable            */
 /* tuning knobs (mainly for tests): "max_bins" (bins per window, default 65536),
  * "pilot_sigmas" (half-width of the pilot bracket in rank sigmas, default 6),
- * "use_pilot" (0: start from the coarse full-range windows), "chunk_samples"
+ * "use_pilot" (0: start from the coarse full-range windows), "sort_samples" (0: fold the
+ * shard in id order instead of pressure-bucket order; same integers either way), "chunk_samples"
  * (granularity of the max_running_time check, default 2^20).                          */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;

@@ -321,6 +321,12 @@ def test_streamed_refinement_paths(vax, ctx):
         assert d.c.n_passes >= 2 and _same(direct, d)
     finally:
         ctx.set_option("max_bins", 65536); ctx.set_option("use_pilot", 1); ctx.set_option("pilot_sigmas", 6.0)
+    try:                                      # regime sort on/off: same integers either way
+        ctx.set_option("sort_samples", 0)
+        e = _run(vax, ctx, bounds, n, 5, direct_max=1, pilot=4096)
+        assert _same(direct, e)
+    finally:
+        ctx.set_option("sort_samples", 1)
     # single-value bounds ([v, v], model.py:376-377): every sample has the same tuple
     deg = np.array([0.4, 0.4, 0.2, 0.2, 0.01, 0.01, 6, 6, 0.011, 0.011, 0.07, 0.07])
     d0 = _run(vax, ctx, deg, 30000, 9, direct_max=1 << 20)
