@@ -39,16 +39,45 @@ DATES = dict(start_date="2020-12-15", end_date="2022-07-1")
 T_DAYS = 564
 N_POP = 50000
 CI_PCT = 95
+# BASELINE.json configs[3]: all bounds x2 width about the same centres, pressure 0-0.1, 5 years
+WIDE = dict(pro=[30, 50], anti=[5.5, 31.5], pressure=[0.0, 0.1], tau=[4, 8], nv0=[0.9, 1.3], nvmax=[2.5, 12.5])
+WIDE_DATES = dict(start_date="2020-12-15", end_date="2025-12-14")
+WIDE_T = 1826
 BYTES_PER_SAMPLE_WEEK = 112.0   # 4 int32 counts per sample-day if materialised
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
-def usa_bounds_frac():
+def bounds_frac(b):
     import numpy as np
 
-    return np.concatenate([np.array(USA["pro"]) / 100, np.array(USA["anti"]) / 100,
-                           np.array(USA["pressure"], dtype=float), np.array(USA["tau"], dtype=float),
-                           np.array(USA["nv0"]) / 100, np.array(USA["nvmax"]) / 100])
+    return np.concatenate([np.array(b["pro"]) / 100, np.array(b["anti"]) / 100,
+                           np.array(b["pressure"], dtype=float), np.array(b["tau"], dtype=float),
+                           np.array(b["nv0"]) / 100, np.array(b["nvmax"]) / 100])
+
+
+def usa_bounds_frac():
+    return bounds_frac(USA)
+
+
+def grid_boxes(n_boxes, seed=20261019):
+    """configs[4]: parameter-bound boxes around the USA centres (generator recorded here):
+    every bound pair = centre * (1 + 0.25*u1) -/+ halfwidth * (0.5 + u2), u ~ U(-1,1) / U(0,1),
+    numpy default_rng(seed); pressure keeps lo = 0."""
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    keys = ["pro", "anti", "pressure", "tau", "nv0", "nvmax"]
+    out = []
+    for _ in range(n_boxes):
+        box = {}
+        for k in keys:
+            lo, hi = USA[k]
+            c, h = (lo + hi) / 2, (hi - lo) / 2
+            c2 = c * (1 + 0.25 * rng.uniform(-1, 1))
+            h2 = h * (0.5 + rng.uniform(0, 1))
+            box[k] = [max(c2 - h2, 0.0), c2 + h2] if k != "pressure" else [0.0, c2 + h2]
+        out.append(box)
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -165,6 +194,61 @@ def run_reference_arm(args):
     return 0
 
 
+def run_grid(args, vax, ctx, rank, world, local_rank, dist):
+    """configs[4]: independent scenarios -> partition BOXES over ranks, no data-path collective."""
+    import numpy as np
+    import torch
+
+    nat = vax._native
+    ci = args.ci if args.ci is not None else 99.0
+    q_lo, q_hi = (1 - ci / 100) / 2.0, (1 + ci / 100) / 2.0
+    boxes = grid_boxes(args.boxes)
+    mine = list(range(rank, args.boxes, world))
+
+    def one_pass(seed0):
+        checksum, ms = 0.0, 0.0
+        for b in mine:
+            cfg = nat.make_config(bounds_frac(boxes[b]), N_POP, T_DAYS, args.samples, seed0 + b, q_lo, q_hi)
+            out = ctx.run_bounds(cfg)
+            assert not out.c.aborted
+            checksum += float(out.mean[0][-1]); ms += out.c.device_ms
+        return checksum, ms
+
+    for i in range(args.warmup):
+        one_pass(10_000 * i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    l0 = ctx.launch_count
+    t0 = time.perf_counter()
+    tot_ms = 0.0
+    for i in range(args.steps):
+        cs, ms = one_pass(1_000_000 + 10_000 * i)
+        tot_ms += ms
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([wall, tot_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        units = args.boxes * args.samples * T_DAYS / 7.0 * args.steps
+        print(json.dumps({
+            "metric": "MC sample-weeks/sec", "value": units / float(t[0].item()), "unit": "sample-weeks/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * float(t[0].item()) / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32 state / fp32 sampler / fp64 arrivals",
+            "data": "synthetic",
+            "config": {"workload": "batched multi-scenario grid (BASELINE configs[4]): %d bound boxes x %g samples, "
+                                   "CI=%g, boxes partitioned over ranks" % (args.boxes, args.samples, ci),
+                       "boxes": args.boxes, "samples_per_box": args.samples, "days": T_DAYS, "N": N_POP,
+                       "generator": "bench.grid_boxes(seed=20261019)"},
+            "device_ms_per_step": float(t[1].item()) / args.steps, "gpu_launches": ctx.launch_count - l0,
+            "timing": "host wall clock around the whole grid incl. D2H of every box's bands (max over ranks)"}))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -173,6 +257,10 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--samples", type=int, default=1_000_000, help="samples per GPU per step")
     ap.add_argument("--cpu-samples", type=int, default=200_000, help="samples of the CPU baseline")
+    ap.add_argument("--workload", default="usa", choices=["usa", "wide5y", "grid"],
+                    help="usa: configs[1]/[2] (use --samples for 1e9/N); wide5y: configs[3]; grid: configs[4]")
+    ap.add_argument("--boxes", type=int, default=1024, help="grid workload: number of bound boxes")
+    ap.add_argument("--ci", type=float, default=None, help="CI in percent (default 95; grid: 99)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -202,8 +290,16 @@ def main():
     dmod = vax.distributed
     ctx = vax.default_context(local_rank)
 
+    if args.workload == "grid":
+        return run_grid(args, vax, ctx, rank, world, local_rank, dist)
+    global T_DAYS, CI_PCT
+    wl_bounds, wl_dates = (USA, DATES) if args.workload == "usa" else (WIDE, WIDE_DATES)
+    if args.workload == "wide5y":
+        T_DAYS = WIDE_T
+    if args.ci is not None:
+        CI_PCT = args.ci
     n_global = args.samples * world
-    bounds = usa_bounds_frac()
+    bounds = bounds_frac(wl_bounds)
     q_lo, q_hi = (1 - CI_PCT / 100) / 2.0, (1 + CI_PCT / 100) / 2.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
 
@@ -213,17 +309,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def all_reduce(t):
-        torch.cuda.current_stream(t.device).synchronize()
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        torch.cuda.current_stream(t.device).synchronize()
+    all_reduce, all_reduce_async = dmod.make_torch_reducers(dist, local_rank) if dist else (None, None)
 
     def one_job(seed):
         cfg = nat.make_config(bounds, N_POP, T_DAYS, n_global, seed, q_lo, q_hi)
         if world == 1:
             return ctx.run_bounds(cfg)
         return dmod.run_sharded(dmod.ContextEngine(ctx), cfg, rank, world, all_reduce,
-                                lambda: nat.ResultBuffers(T_DAYS))
+                                lambda: nat.ResultBuffers(T_DAYS), all_reduce_async)
 
     # ---------------- device-timed leg ("value")
     for i in range(args.warmup):
@@ -262,8 +355,9 @@ def main():
             if dist is not None:
                 dist.barrier()
             t0 = time.perf_counter()
-            res, err, msg = vax.run_model(USA["pro"], USA["anti"], USA["pressure"], USA["tau"], USA["nv0"],
-                                          USA["nvmax"], CI_PCT, n_global, N_POP, DATES, seed=3000 + i)
+            res, err, msg = vax.run_model(wl_bounds["pro"], wl_bounds["anti"], wl_bounds["pressure"],
+                                          wl_bounds["tau"], wl_bounds["nv0"], wl_bounds["nvmax"], CI_PCT,
+                                          n_global, N_POP, wl_dates, seed=3000 + i)
             checksum = float(res["people_vaccinated_per_hundred"]["mean"][-1])  # host read of the result
             dt = time.perf_counter() - t0
             assert err == "" and checksum > 0
@@ -317,8 +411,10 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 state / fp32 sampler / fp64 arrivals", "data": "synthetic",
-        "config": {"workload": "README USA scenario at 1e6 samples per GPU (BASELINE configs[1]); "
-                               "global range = n_gpus x samples_per_gpu, sharded by sample id",
+        "config": {"workload": ("README USA scenario at %g samples per GPU (BASELINE configs[1]); " % args.samples
+                                if args.workload == "usa" else
+                                "wide-uncertainty 5-year sweep at %g samples per GPU (BASELINE configs[3]); " % args.samples)
+                               + "global range = n_gpus x samples_per_gpu, sharded by sample id",
                    "samples_per_gpu": args.samples, "samples_global": n_global, "days": T_DAYS,
                    "N": N_POP, "CI": CI_PCT, "seed": "2000+step", "l2": "flushed between steps (256 MiB memset)",
                    "passes_per_step": statistics.mean(passes) if passes else 0},

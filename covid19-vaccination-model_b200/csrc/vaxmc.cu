@@ -711,7 +711,6 @@ int vx_job_pilot(vx_ctx *ctx)
 {
     if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
     Job *j = ctx->job;
-    if (!j->stats_set) return fail(ctx, VX_ERR_STATE, "vx_job_set_param_stats must precede vx_job_pilot");
     if (j->aborted) return fail(ctx, VX_ERR_STATE, "job aborted by the rejection rule");
     int rc = need_device(ctx);
     if (rc) return rc;
@@ -797,6 +796,8 @@ int vx_job_accumulate(vx_ctx *ctx)
     if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
     Job *j = ctx->job;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_accumulate");
+    if (!j->stats_set) return fail(ctx, VX_ERR_STATE, "vx_job_set_param_stats must precede vx_job_accumulate");
+    if (j->aborted) return fail(ctx, VX_ERR_STATE, "job aborted by the rejection rule");
     if (j->direct || j->finished) return VX_OK;
     int rc = need_device(ctx);
     if (rc) return rc;
@@ -867,6 +868,7 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     int rc = need_device(ctx);
     if (rc) return rc;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_finalize");
+    if (!j->stats_set) return fail(ctx, VX_ERR_STATE, "vx_job_set_param_stats must precede vx_job_finalize");
     Phase ph_(ctx, "finalize");
     if (!j->finished) {
         const int64_t R = j->R;

@@ -84,21 +84,36 @@ class ContextEngine:
         return torch.from_numpy(st).to(f"cuda:{self.ctx.device}")
 
 
-def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out):
-    """Drive one rank of a sharded job.  `all_reduce(tensor)` sums in place across ranks."""
+def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out, all_reduce_async=None):
+    """Drive one rank of a sharded job.
+
+    `all_reduce(tensor)` sums in place across ranks and returns when the result is usable;
+    `all_reduce_async(tensor)` (optional) starts the same reduction and returns a callable that
+    waits for it -- used to hide the small statistics reduction behind the replicated pilot.
+    """
     first, count = shard_range(cfg.n_samples, rank, world)
     engine.begin(cfg, first, count)
     try:
-        st = engine.param_stats()
-        t = engine.stats_tensor(st)
-        all_reduce(t)
-        st = t.cpu().numpy().astype(np.float64)
+        t = engine.stats_tensor(engine.param_stats())
+        wait = all_reduce_async(t) if all_reduce_async is not None else None
+        if wait is None:
+            all_reduce(t)
         out = make_out()
-        if engine.set_param_stats(st):
-            out.c.aborted = 1
-            out.c.n_rejected = int(st[0])
-            return out
-        engine.pilot()
+        if wait is None:
+            st = t.cpu().numpy().astype(np.float64)
+            if engine.set_param_stats(st):
+                out.c.aborted = 1
+                out.c.n_rejected = int(st[0])
+                return out
+            engine.pilot()
+        else:
+            engine.pilot()          # replicated work, overlaps the statistics reduction
+            wait()
+            st = t.cpu().numpy().astype(np.float64)
+            if engine.set_param_stats(st):
+                out.c.aborted = 1
+                out.c.n_rejected = int(st[0])
+                return out
         for _ in range(64):
             engine.accumulate()
             acc = engine.acc_tensor()
@@ -110,6 +125,30 @@ def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out):
         raise RuntimeError("window refinement did not converge")
     finally:
         engine.end()
+
+
+def make_torch_reducers(dist, device):
+    """(all_reduce, all_reduce_async) over torch.distributed for tensors on `device`.
+
+    The library synchronises its own stream before returning from every staged call, so the
+    collective only has to be complete before the next library call."""
+    import torch
+
+    def all_reduce(t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        if t.is_cuda:
+            torch.cuda.current_stream(t.device).synchronize()
+
+    def all_reduce_async(t):
+        work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+
+        def wait():
+            work.wait()
+            if t.is_cuda:
+                torch.cuda.current_stream(t.device).synchronize()
+        return wait
+
+    return all_reduce, all_reduce_async
 
 
 def run_job(cfg, device=None):
@@ -129,12 +168,6 @@ def run_job(cfg, device=None):
     ctx = nat.default_context(int(device))
     if world == 1:
         return ctx.run_bounds(cfg)
-    import torch
-
-    def all_reduce(t):
-        torch.cuda.current_stream(t.device).synchronize()
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        torch.cuda.current_stream(t.device).synchronize()
-
+    all_reduce, all_reduce_async = make_torch_reducers(dist, ctx.device)
     return run_sharded(ContextEngine(ctx), cfg, dist.get_rank(), world, all_reduce,
-                       lambda: nat.ResultBuffers(cfg.T))
+                       lambda: nat.ResultBuffers(cfg.T), all_reduce_async)

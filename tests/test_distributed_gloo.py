@@ -104,7 +104,11 @@ def _worker(rank, world, port, n, q):
 
         out = d.run_sharded(eng, _Cfg(n), rank, world, all_reduce, _Out)
         bad = FakeEngine(infeasible=True)
-        out_bad = d.run_sharded(bad, _Cfg(n), rank, world, all_reduce, _Out)
+        _, all_reduce_async = d.make_torch_reducers(dist, None)
+        out_bad = d.run_sharded(bad, _Cfg(n), rank, world, all_reduce, _Out, all_reduce_async)
+        eng2 = FakeEngine()
+        out2 = d.run_sharded(eng2, _Cfg(n), rank, world, all_reduce, _Out, all_reduce_async)
+        assert np.array_equal(out2.merged, out.merged) and eng2.calls[1] == ("pilot",)
         q.put((rank, out.merged.tolist(), eng.gstats.tolist(), eng.passes, n_reduces[0], eng.calls,
                out_bad.c.aborted, bad.passes))
     finally:
@@ -147,7 +151,7 @@ def test_two_rank_gloo_merge_equals_single_rank(n):
         assert np.array_equal(np.array(m), merged)              # integer merge is exact
         assert np.allclose(st, stats, rtol=1e-14)
         assert passes == 2                                       # one VX_REFINE round trip
-        assert n_red == 1 + 2 + 1                                # stats + one per pass (+ abort job's stats)
+        assert n_red == 1 + 2 + 2                                # stats + one per pass, twice (async stats not counted)
         assert calls[0][0] == "begin" and calls[1] == ("pilot",) and calls[-1] == ("end",)
         assert aborted == 1 and bad_passes == 0                  # abort path: no pass is run
 
