@@ -321,9 +321,10 @@ def main():
     # ---------------- device-timed leg ("value")
     for i in range(args.warmup):
         one_job(1000 + i)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.15)
+    sampler = ClockSampler(local_rank)      # rank 0 only: nvidia-smi takes driver locks
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
     barrier()
     launches0 = ctx.launch_count
     dev_ms, fold_ms, pilot_ms, fold_launches, passes = [], [], [], 0, []
@@ -337,7 +338,7 @@ def main():
     barrier()
     wall_s = time.perf_counter() - t_wall0
     launches = ctx.launch_count - launches0
-    clocks = sampler.finish()
+    clocks = sampler.finish() if rank == 0 else None
 
     tot_ms = torch.tensor([sum(dev_ms)], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:

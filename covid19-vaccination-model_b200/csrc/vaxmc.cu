@@ -450,10 +450,18 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
     return VX_OK;
 }
 
-int64_t default_pilot(int64_t n)
+// Pilot size.  The pilot is replicated on every rank and its stepper is latency-bound (one
+// 564-day dependency chain per warp, ~0.4 ms however few samples), the select pass scales
+// with n_p, and the window width -- hence the slab the ranks all-reduce -- with n_p^-1/2.
+// The fold's slow path costs ~1 % of the fold at n_p = 32768 (windows hold ~1 % of the mass),
+// so a bigger pilot buys nothing; it only has to be big enough that the +-6 sigma bracket of
+// the outer quantile stays inside the pilot sample: n_p * q_tail >~ 64.
+int64_t default_pilot(double q_lo, double q_hi)
 {
-    int64_t p = 32768;
-    while (p < n / 32 && p < ((int64_t)1 << 20)) p <<= 1;
+    double tail = std::min(std::min(q_lo, 1.0 - q_lo), std::min(q_hi, 1.0 - q_hi));
+    tail = std::max(tail, 1e-9);
+    int64_t p = 16384;
+    while ((double)p * tail < 64.0 && p < ((int64_t)1 << 20)) p <<= 1;
     return p;
 }
 
@@ -739,7 +747,7 @@ int vx_job_pilot(vx_ctx *ctx)
         j->n_pilot = 0;
         return plan_windows(ctx, false);
     }
-    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(n));
+    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(j->cfg.q_lo, j->cfg.q_hi));
     j->n_pilot = np;
     if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * R * np, &p_); if (rc_) return rc_; j->d_dump = (int32_t *)p_; }
