@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "vaxmc.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "vaxmc_kernels.cuh"), os.path.join(ROOT, "include", "vaxmc.h")]
-LIB = os.path.join(HERE, "libvaxmc.so")
+LIB = os.environ.get("VAXMC_LIB") or os.path.join(HERE, "libvaxmc.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -38,7 +38,8 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [find_nvcc(), *NVCC_FLAGS, "-o", LIB, SRC]
+    extra = os.environ.get("VAXMC_NVCC_EXTRA", "").split()
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, SRC]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)

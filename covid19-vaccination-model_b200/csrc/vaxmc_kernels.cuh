@@ -370,11 +370,14 @@ constexpr int ACC_HDR = 8;
 constexpr int WIN_DAYS = 14;       // one warp tile = 2 weeks = 14+14+2+2 = 32 rows
 constexpr int TILE_LD = 33;        // padded leading dimension: conflict-free both ways
 constexpr int SIM_THREADS = 128;       // warps are independent: small CTAs = short tail
+#ifndef VX_SIM_MINBLOCKS
+#define VX_SIM_MINBLOCKS 8            // CTAs per SM the register allocation is capped for
+#endif
 
 enum { SIM_DUMP = 0, SIM_FOLD = 1 };
 
 template <int MODE>
-__global__ void __launch_bounds__(SIM_THREADS, 8) vx_sim_kernel(const SimArgs a)
+__global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(const SimArgs a)
 {
     __shared__ int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -234,7 +234,7 @@ def test_ks_per_week_against_oracle_on_identical_parameters(vax, ctx):
     """north_star check (2): identical sampled parameter sets, matched sample counts, two-sample
     KS per weekly date and series between the CUDA path and the numpy-law oracle."""
     bounds = usa_bounds_frac()
-    n = 60000
+    n = int(os.environ.get("VX_KS_SAMPLES", "60000"))     # configs[1] full size: VX_KS_SAMPLES=1000000
     cfg = _cfg(vax, bounds, n, seed=4242)
     params, _ = ctx.sample_params(cfg, 0, n)
     counts = ctx.dump_counts(cfg, 0, n)
@@ -254,10 +254,50 @@ def test_ks_per_week_against_oracle_on_identical_parameters(vax, ctx):
     assert pvals.min() > 0.01 / len(pvals), pvals.min()           # Bonferroni: no week rejects
     assert (pvals < 0.01).mean() <= 0.03, (pvals < 0.01).mean()   # chance level of p<0.01
     assert stats.kstest(pvals, "uniform").pvalue > 1e-4 or np.median(pvals) > 0.3
+    print(f"\nKS per week: n={n} per arm, {len(pvals)} (series, week) tests, min p={pvals.min():.4f}, "
+          f"median p={np.median(pvals):.3f}, share p<0.01: {(pvals < 0.01).mean():.4f}")
     # the per-sample difference has zero mean within Monte Carlo error (same tuples -> paired)
     for r in (100, 300, 563, T + 20, T + 60, T + 2 * W + 300):
         diff = counts[r].astype(np.float64) - orc[r]
         assert abs(diff.mean()) < 5 * diff.std() / np.sqrt(n) + 1e-9, r
+
+
+@pytest.mark.parametrize("tuple_", [
+    (0.4, 0.2, 0.01, 6.0, 0.011, 0.07),        # SURVEY 8c tuple
+    (0.36, 0.24, 0.0005, 5.2, 0.0101, 0.052),  # tiny pressure: lam2 in the inversion regime
+    (0.30, 0.055, 0.1, 4.0, 0.009, 0.125),     # wide-sweep corner, strong pressure
+])
+def test_ks_per_week_pure_sampler_noise(vax, ctx, tuple_):
+    """Sharper than the mixed-parameter KS: EVERY sample has the same tuple, so the spread across
+    samples is nothing but the Poisson draws.  CUDA sampler (inversion < 4, CF expansion above)
+    vs numpy's algorithms (multiplication method < 10, PTRS above) in the oracle."""
+    n = 200_000
+    params = np.tile(np.array(tuple_, dtype=np.float64), (n, 1))
+    cfg = _cfg(vax, np.zeros(12), n, seed=99)
+    out, counts = ctx.run_params(vax._native.make_config(np.zeros(12), 50000, USA_T, n, 99, 0.025, 0.975,
+                                                         direct_max=1 << 20), params, want_counts=True)
+    d, w = ro.bulk_counts(4321, params, USA_T, 50000, threads=os.cpu_count())
+    orc = _oracle_rows(d, w, USA_T, USA_W)
+    T, W = USA_T, USA_W
+    assert np.array_equal(counts[T + W:T + 2 * W], orc[T + W:T + 2 * W])      # deliveries: bit-exact
+    rows = np.concatenate([np.arange(0, T, 7), T + np.arange(W), T + 2 * W + np.arange(0, T, 7)])
+    pvals = []
+    for r in rows:
+        a, b = counts[r], orc[r]
+        if a.min() == a.max() and b.min() == b.max():
+            assert a[0] == b[0]
+            continue
+        pvals.append(stats.ks_2samp(a, b, method="asymp").pvalue)
+        # first two moments agree within Monte Carlo error
+        sd = max(a.std(), b.std(), 1e-9)
+        assert abs(a.mean() - b.mean()) < 6 * sd * np.sqrt(2 / n) + 1e-9, r
+        assert abs(a.std() - b.std()) < 6 * sd / np.sqrt(n) + 0.02 * sd + 1e-9, r
+    pvals = np.array(pvals)
+    assert len(pvals) > 150
+    assert pvals.min() > 0.01 / len(pvals), pvals.min()
+    assert (pvals < 0.01).mean() <= 0.04, (pvals < 0.01).mean()
+    print(f"\npure-noise KS {tuple_}: {len(pvals)} tests, min p={pvals.min():.4f}, median p={np.median(pvals):.3f}, "
+          f"share p<0.01: {(pvals < 0.01).mean():.4f}")
 
 
 def test_bands_agree_with_reference_fixture_within_mc_error(vax, golden_dir):
