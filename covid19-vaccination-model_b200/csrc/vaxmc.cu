@@ -75,6 +75,8 @@ struct Job {
     int64_t n_total = 0;                  // samples folded (all ranks) = number_finished_samples
     int64_t shard_done = 0;               // samples of this shard folded in pass 1
     int n_passes = 0;
+    int32_t *d_perm = nullptr;            // pressure-bucket order of the shard (first pass, untimed jobs)
+    int64_t perm_first = 0, perm_count = 0;
     // results (host)
     std::vector<double> mean[4], lower[4], upper[4];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -96,6 +98,8 @@ struct vx_ctx {
     bool trace = false;
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t side = nullptr;          // regime sort runs here, under the latency-bound pilot
+    cudaEvent_t side_done = nullptr;
     std::string err;
     int64_t launches = 0;
     Job *job = nullptr;
@@ -456,6 +460,28 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
 // The fold's slow path costs ~1 % of the fold at n_p = 32768 (windows hold ~1 % of the mass),
 // so a bigger pilot buys nothing; it only has to be big enough that the +-6 sigma bracket of
 // the outer quantile stays inside the pilot sample: n_p * q_tail >~ 64.
+// Counting sort of samples [first, first+count) by pressure bucket into d_perm (local ids).
+int launch_regime_sort(vx_ctx *ctx, Job *j, int64_t first, int64_t count, cudaStream_t st, int32_t **perm_out)
+{
+    void *p_ = nullptr;
+    int rc = pool_get(ctx, SLOT_PERM, sizeof(int32_t) * count, &p_);
+    if (rc) return rc;
+    int32_t *d_perm = (int32_t *)p_;
+    rc = pool_get(ctx, SLOT_SORT, sizeof(uint32_t) * SORT_BUCKETS, &p_);
+    if (rc) return rc;
+    uint32_t *d_cnt = (uint32_t *)p_;
+    const unsigned sgrid = (unsigned)((count + 255) / 256);
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * SORT_BUCKETS, st));
+    vx_bucket_count_kernel<<<sgrid, 256, 0, st>>>(j->cfg.seed, first, count, d_cnt);
+    CKL();
+    vx_bucket_scan_kernel<<<1, SORT_BUCKETS, 0, st>>>(d_cnt);
+    CKL();
+    vx_bucket_scatter_kernel<<<sgrid, 256, 0, st>>>(j->cfg.seed, first, count, d_cnt, d_perm);
+    CKL();
+    *perm_out = d_perm;
+    return VX_OK;
+}
+
 int64_t default_pilot(double q_lo, double q_hi)
 {
     double tail = std::min(std::min(q_lo, 1.0 - q_lo), std::min(q_hi, 1.0 - q_hi));
@@ -537,6 +563,8 @@ int vx_create(vx_ctx **out, int device)
     c->trace = getenv("VX_TRACE") != nullptr;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int sm = 0;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
@@ -556,6 +584,8 @@ void vx_destroy(vx_ctx *ctx)
     free_job(ctx);
     pool_release(ctx);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->side) cudaStreamDestroy(ctx->side);
+    if (ctx->side_done) cudaEventDestroy(ctx->side_done);
     delete ctx;
 }
 
@@ -749,6 +779,17 @@ int vx_job_pilot(vx_ctx *ctx)
     }
     const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(j->cfg.q_lo, j->cfg.q_hi));
     j->n_pilot = np;
+    if (!j->direct && ctx->sort_samples && !j->explicit_params && !(j->cfg.max_running_time > 0.0)) {
+        // the part of the shard the stepper will fold (the pilot's own samples come from its matrix):
+        // sort it now, on the side stream, while the pilot stepper leaves the GPU mostly idle
+        const int64_t lo = std::max(j->shard_first, np), hi = j->shard_first + j->shard_count;
+        if (hi - lo >= 4096 && hi - lo <= ((int64_t)1 << 30)) {
+            rc = launch_regime_sort(ctx, j, lo, hi - lo, ctx->side, &j->d_perm);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->side_done, ctx->side));
+            j->perm_first = lo; j->perm_count = hi - lo;
+        }
+    }
     if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * R * np, &p_); if (rc_) return rc_; j->d_dump = (int32_t *)p_; }
     { Phase ph2_(ctx, "  pilot stepper"); rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np); }
@@ -831,22 +872,15 @@ int vx_job_accumulate(vx_ctx *ctx)
                               j->d_params ? j->d_params + 6 * (j->shard_first + done) : nullptr);
         a.wins = j->d_wins;
         a.acc = j->d_acc;
-        if (ctx->sort_samples && !j->explicit_params && cnt >= 4096) {
-            // counting sort of the chunk by pressure bucket -> lanes of a warp share a regime
-            void *p_ = nullptr;
-            rc = pool_get(ctx, SLOT_PERM, sizeof(int32_t) * cnt, &p_); if (rc) return rc;
-            int32_t *d_perm = (int32_t *)p_;
-            rc = pool_get(ctx, SLOT_SORT, sizeof(uint32_t) * SORT_BUCKETS, &p_); if (rc) return rc;
-            uint32_t *d_cnt = (uint32_t *)p_;
-            const unsigned sgrid = (unsigned)((cnt + 255) / 256);
-            CK(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * SORT_BUCKETS, ctx->stream));
-            vx_bucket_count_kernel<<<sgrid, 256, 0, ctx->stream>>>(j->cfg.seed, a.first, cnt, d_cnt);
-            CKL();
-            vx_bucket_scan_kernel<<<1, SORT_BUCKETS, 0, ctx->stream>>>(d_cnt);
-            CKL();
-            vx_bucket_scatter_kernel<<<sgrid, 256, 0, ctx->stream>>>(j->cfg.seed, a.first, cnt, d_cnt, d_perm);
-            CKL();
+        if (j->d_perm && j->perm_first == a.first && j->perm_count == cnt) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));
+            a.perm = j->d_perm;
+        } else if (ctx->sort_samples && !j->explicit_params && cnt >= 4096) {
+            int32_t *d_perm = nullptr;
+            rc = launch_regime_sort(ctx, j, a.first, cnt, ctx->stream, &d_perm);
+            if (rc) return rc;
             a.perm = d_perm;
+            j->d_perm = nullptr;      // the pool slot now holds this chunk's order
         }
         const int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
         vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);

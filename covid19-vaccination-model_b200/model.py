@@ -23,6 +23,7 @@ pandas is used for dates only (model.py:171, 211), exactly as in the reference.
 from __future__ import annotations
 
 import argparse
+import functools
 import json
 import os
 import time
@@ -62,6 +63,7 @@ def _next_seed(explicit: int | None) -> tuple[int, bool]:
 
 
 # --------------------------------------------------------------------------- dates
+@functools.lru_cache(maxsize=64)
 def _dates(start_date, end_date):
     daily = pd.date_range(start_date, end_date, freq="1D")            # model.py:171
     weekly = pd.date_range(start=start_date, end=end_date, freq="7D")  # model.py:211

@@ -291,9 +291,11 @@ def test_ks_per_week_pure_sampler_noise(vax, ctx, tuple_):
         # first two moments agree within Monte Carlo error
         sd = max(a.std(), b.std(), 1e-9)
         assert abs(a.mean() - b.mean()) < 6 * sd * np.sqrt(2 / n) + 1e-9, r
-        assert abs(a.std() - b.std()) < 6 * sd / np.sqrt(n) + 0.02 * sd + 1e-9, r
+        m4 = max(((a - a.mean()) ** 4).mean(), ((b - b.mean()) ** 4).mean())
+        se_sd = np.sqrt(max(m4 - sd ** 4, 0.0) / (4 * n * sd * sd)) * np.sqrt(2)   # delta method
+        assert abs(a.std() - b.std()) < 6 * se_sd + 1e-9, r
     pvals = np.array(pvals)
-    assert len(pvals) > 150
+    assert len(pvals) > 100      # rows that are constant in both arms carry no test
     assert pvals.min() > 0.01 / len(pvals), pvals.min()
     assert (pvals < 0.01).mean() <= 0.04, (pvals < 0.01).mean()
     print(f"\npure-noise KS {tuple_}: {len(pvals)} tests, min p={pvals.min():.4f}, median p={np.median(pvals):.3f}, "
