@@ -45,6 +45,10 @@ WIDE_DATES = dict(start_date="2020-12-15", end_date="2025-12-14")
 WIDE_T = 1826
 BYTES_PER_SAMPLE_WEEK = 112.0   # 4 int32 counts per sample-day if materialised
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+# from profiles/r01_fold_vd_ncu_summary.txt (ncu --set full of this kernel, this workload, 1e6 samples)
+NCU_WARP_INST_PER_WARP_DAY = 227.2   # smsp__inst_executed.sum / (samples*days/32)
+NCU_DRAM_BYTES_PER_LAUNCH = 2.66e7   # dram__bytes_read.sum + dram__bytes_write.sum
+N_SM, SCHEDULERS_PER_SM = 148, 4
 
 
 def bounds_frac(b):
@@ -388,7 +392,9 @@ def main():
     roofline = {
         "kernel": "vx_sim_kernel<SIM_FOLD>", "bound": "hbm",
         "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+        "frac": (achieved / peak) if achieved else None,
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (args.samples / 1e6) if args.workload == "usa" else None,
+        "peak_source": peak_src,
         "ms_per_launch": fold_ms_avg, "share_of_step": sum(fold_ms) / sum(dev_ms) if sum(dev_ms) else None,
         "note": ("algorithmic bytes = 112 B per sample-week (the int32 trajectories of SURVEY.md 8d) x "
                  "sample-weeks per launch; the kernel folds them on the fly instead of writing them, so "
@@ -396,8 +402,16 @@ def main():
                  "is ~0 by design"),
     }
     sd_per_s = args.samples * T_DAYS / (fold_ms_avg * 1e-3) if fold_launches else None
-    issue = {"sample_days_per_s_per_gpu": sd_per_s,
-             "note": "issue-slot utilisation of the stepper is read from profiles/ (ncu sm__inst_executed)"}
+    sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
+    issue_peak = N_SM * SCHEDULERS_PER_SM * sm_hz                      # warp-instructions/s the SMs can issue
+    issue_ach = NCU_WARP_INST_PER_WARP_DAY * (sd_per_s / 32.0) if sd_per_s else None
+    issue = {"bound": "issue", "sample_days_per_s_per_gpu": sd_per_s,
+             "warp_inst_per_warp_day": NCU_WARP_INST_PER_WARP_DAY,
+             "achieved": issue_ach, "peak": issue_peak, "unit": "warp-inst/s",
+             "frac": (issue_ach / issue_peak) if issue_ach else None,
+             "note": "the stepper's real roofline: warp instructions issued per second (instruction count per "
+                     "warp-day from the ncu capture in profiles/, rate from this run's CUDA events) over "
+                     "148 SMs x 4 schedulers x the SM clock sampled during the run"}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -342,6 +342,31 @@ def test_streamed_equals_direct(vax, ctx, q):
     assert _same(direct, streamed)
 
 
+@pytest.mark.parametrize("case", [
+    dict(T=1, n=4097, N=50000, bounds="usa"),                      # a single day
+    dict(T=13, n=5000, N=50000, bounds="usa"),                     # less than one 14-day tile
+    dict(T=15, n=33, N=50000, bounds="usa"),                       # fewer samples than the pilot
+    dict(T=100, n=40001, N=1000, bounds="usa"),                    # ragged warp, tiny population
+    dict(T=371, n=20000, N=1000000, bounds="wide"),                # lam up to ~1e5, deliveries ~1e6
+    dict(T=200, n=30000, N=50000, bounds="reject"),                # rejection-heavy parameter draw
+    dict(T=564, n=131073, N=50000, bounds="usa", q=(0.1, 0.9)),    # just above the default direct_max
+])
+def test_streamed_equals_direct_edge_shapes(vax, ctx, case):
+    b = {"usa": usa_bounds_frac(), "wide": wide_bounds_frac(),
+         "reject": np.array([0.5, 0.9, 0.3, 0.6, 0.0, 0.1, 3, 4, 0.002, 0.0024, 0.1, 0.1])}[case["bounds"]]
+    q = case.get("q", (0.025, 0.975))
+    kw = dict(T=case["T"], N=case["N"], q=q)
+    direct = _run(vax, ctx, b, case["n"], 17, direct_max=1 << 22, **kw)
+    streamed = _run(vax, ctx, b, case["n"], 17, direct_max=1, pilot=2048, **kw)
+    assert direct.c.n_passes == 0 and streamed.c.n_passes >= 1
+    assert _same(direct, streamed)
+    assert streamed.c.n_rejected == direct.c.n_rejected
+    if case["bounds"] == "reject":
+        assert direct.c.n_rejected > 0
+    default = _run(vax, ctx, b, case["n"], 17, direct_max=0, **kw)      # library's own choice of path
+    assert _same(direct, default)
+
+
 def test_streamed_refinement_paths(vax, ctx):
     """Tiny windows / no pilot / degenerate bounds force the VX_REFINE loop; still exact."""
     bounds = usa_bounds_frac()
