@@ -293,6 +293,9 @@ def main():
     nat = vax._native
     dmod = vax.distributed
     ctx = vax.default_context(local_rank)
+    for kv in filter(None, os.environ.get("VX_OPTIONS", "").split(",")):   # e.g. VX_OPTIONS=fold_pad_smem=20000
+        k, v = kv.split("=")
+        ctx.set_option(k, float(v))
 
     if args.workload == "grid":
         return run_grid(args, vax, ctx, rank, world, local_rank, dist)

@@ -109,6 +109,7 @@ struct vx_ctx {
     double pilot_sigmas = 6.0;
     int64_t use_pilot = 1;
     int64_t sort_samples = 1;
+    int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
     int sm_count = 148;
 };
 
@@ -610,6 +611,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "pilot_sigmas") { if (!(value >= 0)) return fail(ctx, VX_ERR_ARG, "pilot_sigmas < 0"); ctx->pilot_sigmas = value; }
     else if (s == "use_pilot") ctx->use_pilot = value != 0;
     else if (s == "sort_samples") ctx->sort_samples = value != 0;
+    else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }
@@ -883,7 +885,7 @@ int vx_job_accumulate(vx_ctx *ctx)
             j->d_perm = nullptr;      // the pool slot now holds this chunk's order
         }
         const int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
-        vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+        vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, (size_t)ctx->fold_pad_smem, ctx->stream>>>(a);
         CKL();
         j->fold_launches++;
         done += cnt;
