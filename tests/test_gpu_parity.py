@@ -367,6 +367,24 @@ def test_streamed_equals_direct_edge_shapes(vax, ctx, case):
     assert _same(direct, default)
 
 
+def test_explicit_tuples_streamed_equals_direct(vax, ctx):
+    """run_sampling's tuple-driven form (vx_run_params) through the pilot + streaming fold."""
+    nat = vax._native
+    bounds = usa_bounds_frac()
+    n = 30011
+    params, _ = ctx.sample_params(_cfg(vax, bounds, n, seed=8), 0, n)
+    a = ctx.run_params(nat.make_config(np.zeros(12), 50000, 150, n, 8, 0.025, 0.975, direct_max=1 << 20), params)
+    b = ctx.run_params(nat.make_config(np.zeros(12), 50000, 150, n, 8, 0.025, 0.975, direct_max=1,
+                                       pilot_samples=2048), params)
+    assert a.c.n_passes == 0 and b.c.n_passes >= 1 and _same(a, b)
+    # and the bounds-driven job on the same seed draws the very same tuples
+    c = ctx.run_bounds(_cfg(vax, bounds, n, seed=8, T=150, direct_max=1, pilot_samples=2048))
+    assert _same(a, c)
+    with pytest.raises(nat.VaxmcError):                       # assert p_pro + p_anti <= 1 (model.py:63)
+        bad = params.copy(); bad[5, 0] = 0.9; bad[5, 1] = 0.2
+        ctx.run_params(nat.make_config(np.zeros(12), 50000, 150, n, 8, 0.025, 0.975), bad)
+
+
 def test_streamed_refinement_paths(vax, ctx):
     """Tiny windows / no pilot / degenerate bounds force the VX_REFINE loop; still exact."""
     bounds = usa_bounds_frac()
