@@ -139,18 +139,20 @@ constexpr float CF_B0 = 0.00125185f, CF_B2 = -0.01826666f, CF_B4 = 0.00198713f, 
 
 __device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
 {
-    const float rs = fast_rsqrt(lam), s = lam * rs, z2 = z * z, rl = rs * rs;
+    // Horner in w = lam^-1/2:  Q = lam + s z + c0 + w (c1 + w (c2 + w (c3 + w c4)))
+    const float w1 = fast_rsqrt(lam), s = lam * w1, z2 = z * z;
     // the two fitted orders only matter for small lam; evaluate them at |z| <= 5 so that the
     // odd/even degree-5/6 polynomials cannot bend Q back in the far tails
     const float zc = fminf(fmaxf(z, -5.0f), 5.0f), zc2 = zc * zc;
-    float q = fmaf(s, z, fmaf(z2, 0.16666667f, 0.33333334f));   // + lam added last
-    q = fmaf(rs * z, fmaf(z2, -0.013888889f, -0.027777778f), q);
-    q = fmaf(rl, fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f), q);
-    q = fmaf(rl * rs * zc, fmaf(zc2, fmaf(zc2, CF_A5, CF_A3), CF_A1), q);
-    q = fmaf(rl * rl, fmaf(zc2, fmaf(zc2, fmaf(zc2, CF_B6, CF_B4), CF_B2), CF_B0), q);
-    // lam + q in fp32: at lam = 1e5 one ulp is 0.008, i.e. a 1e-5 shift of the CDF -- below the
-    // expansion's own error; rounding to nearest keeps it unbiased
-    int x = max(__float2int_rd(lam + q), 0);
+    const float c0 = fmaf(z2, 0.16666667f, 0.33333334f);
+    const float c1 = z * fmaf(z2, -0.013888889f, -0.027777778f);
+    const float c2 = fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f);
+    const float c3 = zc * fmaf(zc2, fmaf(zc2, CF_A5, CF_A3), CF_A1);
+    const float c4 = fmaf(zc2, fmaf(zc2, fmaf(zc2, CF_B6, CF_B4), CF_B2), CF_B0);
+    const float tail = fmaf(w1, fmaf(w1, fmaf(w1, fmaf(w1, c4, c3), c2), c1), c0);
+    // lam + s z + tail in fp32: at lam = 1e5 one ulp is 0.008, i.e. a 1e-5 shift of the CDF --
+    // below the expansion's own error; rounding to nearest keeps it unbiased
+    int x = max(__float2int_rd(fmaf(s, z, lam) + tail), 0);
     if (lam < POISSON_INV_MAX) {
         x = 0;
         if (lam > 0.0f) {
@@ -368,7 +370,7 @@ struct SimArgs {
 
 constexpr int ACC_HDR = 8;
 constexpr int WIN_DAYS = 14;       // one warp tile = 2 weeks = 14+14+2+2 = 32 rows
-constexpr int TILE_LD = 33;        // padded leading dimension: conflict-free both ways
+constexpr int TILE_LD = 36;        // padded, 16 B-aligned rows: sample-major STS and row-major LDS.128 are both conflict-free
 constexpr int SIM_THREADS = 128;       // warps are independent: small CTAs = short tail
 #ifndef VX_SIM_MINBLOCKS
 #define VX_SIM_MINBLOCKS 8            // CTAs per SM the register allocation is capped for
@@ -379,7 +381,7 @@ enum { SIM_DUMP = 0, SIM_FOLD = 1 };
 template <int MODE>
 __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(const SimArgs a)
 {
-    __shared__ int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 1];
+    __shared__ __align__(16) int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t warp_base = (int64_t)blockIdx.x * SIM_THREADS + warp * 32;
     if (warp_base >= a.count) return;                       // warp-uniform
@@ -418,6 +420,7 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
 
     const int T = a.T, W = a.W;
     for (int d0 = 0; d0 < T; d0 += WIN_DAYS) {
+        int *tp = tile + lane;                              // this sample's column of the tile
 #pragma unroll 1
         for (int wk = 0; wk < 2; ++wk) {
             const int dw = d0 + 7 * wk;
@@ -451,8 +454,9 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
                 n_agn -= da; n_wait += da;
                 // ---- recording, model.py:124-127 and the weekly series :196-214
                 if (MODE == SIM_FOLD) {
-                    tile[(7 * wk + dd) * TILE_LD + lane] = n_vacc;
-                    tile[(14 + 7 * wk + dd) * TILE_LD + lane] = stock;
+                    tp[0] = n_vacc;
+                    tp[14 * TILE_LD] = stock;
+                    tp += TILE_LD;
                     if (dd == 0) {
                         tile[(28 + wk) * TILE_LD + lane] = dv + q0;
                         tile[(30 + wk) * TILE_LD + lane] = received;
@@ -514,7 +518,8 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
                 int s = 0;
 #pragma unroll 1
                 for (; s + 4 <= nvalid; s += 4) {
-                    const int v0 = row[s], v1 = row[s + 1], v2 = row[s + 2], v3 = row[s + 3];
+                    const int4 v4 = *reinterpret_cast<const int4 *>(row + s);
+                    const int v0 = v4.x, v1 = v4.y, v2 = v4.z, v3 = v4.w;
                     sum += (uint32_t)v0 + (uint32_t)v1 + (uint32_t)v2 + (uint32_t)v3;
                     const uint32_t l0 = v0 - wl.a, l1 = v1 - wl.a, l2 = v2 - wl.a, l3 = v3 - wl.a;
                     const uint32_t h0 = v0 - wh.a, h1 = v1 - wh.a, h2 = v2 - wh.a, h3 = v3 - wh.a;
