@@ -364,6 +364,7 @@ struct SimArgs {
     int32_t *dump;          // DUMP: [R][dump_stride] raw rows, column = local sample
     int64_t dump_stride;
     const int32_t *perm;    // FOLD: optional order of the local samples (pressure-sorted), or nullptr
+    int persist;            // FOLD: warps claim 32-sample batches from acc[1] until the shard is done
     const Win *wins;        // FOLD: [R][2]
     unsigned long long *acc;// FOLD: header(8) | sums[R] | below[R][2] | hist bins
 };
@@ -383,7 +384,14 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
 {
     __shared__ __align__(16) int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t warp_base = (int64_t)blockIdx.x * SIM_THREADS + warp * 32;
+    int64_t warp_base = (int64_t)blockIdx.x * SIM_THREADS + warp * 32;
+    const bool persist = (MODE == SIM_FOLD) && a.persist;
+  for (;;) {   // persistent FOLD launch: one resident warp per slot, dynamic batches (no grid tail)
+    if (persist) {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(a.acc + 1, 32ull);
+        warp_base = (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    }
     if (warp_base >= a.count) return;                       // warp-uniform
     const int nvalid = (int)min((int64_t)32, a.count - warp_base);
     const bool live = lane < nvalid;
@@ -546,6 +554,8 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
     }
     if (MODE == SIM_FOLD && lane == 0)
         atomicAdd(a.acc + 0, (unsigned long long)nvalid);  // header word 0: samples folded
+    if (!persist) return;
+  }
 }
 
 // Fold of an already materialised block of raw rows (the pilot matrix) into the accumulator
@@ -763,16 +773,31 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
             }
         }
         __syncthreads();
-        if (tid < nranks) {
-            const uint32_t *h = hist[hid[tid]];
-            long long r = rem[tid], cum = 0;
-            int b = 0;
-            for (; b < 255; ++b) {
-                if (r < cum + (long long)h[b]) break;
-                cum += h[b];
+        if ((tid >> 5) < nranks) {           // warp w locates rank w in its 256-bin histogram
+            const int w = tid >> 5, l = tid & 31;
+            const uint32_t *h = hist[hid[w]] + 8 * l;
+            uint32_t c[8], lsum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = h[i]; lsum += c[i]; }
+            long long incl = lsum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (l >= o) incl += y;
             }
-            rem[tid] = r - cum;
-            prefix[tid] = (prefix[tid] << 8) | (key_t)b;
+            const long long excl = incl - lsum, r = rem[w];
+            const uint32_t m = __ballot_sync(0xffffffffu, r >= excl && r < incl);
+            const int src = m ? __ffs(m) - 1 : 31;
+            if (l == src) {
+                long long cum = excl;
+                int i = 0;
+                for (; i < 7; ++i) {
+                    if (r < cum + (long long)c[i]) break;
+                    cum += c[i];
+                }
+                rem[w] = r - cum;
+                prefix[w] = (prefix[w] << 8) | (key_t)(8 * l + i);
+            }
         }
         __syncthreads();
     }
