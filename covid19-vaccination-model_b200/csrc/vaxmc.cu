@@ -110,7 +110,6 @@ struct vx_ctx {
     int64_t use_pilot = 1;
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
-    int64_t persistent = 1;
     int sm_count = 148;
 };
 
@@ -613,7 +612,6 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "use_pilot") ctx->use_pilot = value != 0;
     else if (s == "sort_samples") ctx->sort_samples = value != 0;
     else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
-    else if (s == "persistent") ctx->persistent = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }
@@ -886,12 +884,7 @@ int vx_job_accumulate(vx_ctx *ctx)
             a.perm = d_perm;
             j->d_perm = nullptr;      // the pool slot now holds this chunk's order
         }
-        int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
-        const int64_t resident = (int64_t)ctx->sm_count * VX_SIM_MINBLOCKS;
-        if (ctx->persistent && !timed && cnt == todo - done && grid > resident) {
-            a.persist = 1;      // acc[1] (zeroed with the slab) is the batch counter of this launch
-            grid = resident;
-        }
+        const int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
         vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, (size_t)ctx->fold_pad_smem, ctx->stream>>>(a);
         CKL();
         j->fold_launches++;

@@ -364,7 +364,6 @@ struct SimArgs {
     int32_t *dump;          // DUMP: [R][dump_stride] raw rows, column = local sample
     int64_t dump_stride;
     const int32_t *perm;    // FOLD: optional order of the local samples (pressure-sorted), or nullptr
-    int persist;            // FOLD: warps claim 32-sample batches from acc[1] until the shard is done
     const Win *wins;        // FOLD: [R][2]
     unsigned long long *acc;// FOLD: header(8) | sums[R] | below[R][2] | hist bins
 };
@@ -384,14 +383,9 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
 {
     __shared__ __align__(16) int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int64_t warp_base = (int64_t)blockIdx.x * SIM_THREADS + warp * 32;
-    const bool persist = (MODE == SIM_FOLD) && a.persist;
-  for (;;) {   // persistent FOLD launch: one resident warp per slot, dynamic batches (no grid tail)
-    if (persist) {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(a.acc + 1, 32ull);
-        warp_base = (int64_t)__shfl_sync(0xffffffffu, t, 0);
-    }
+    // (a persistent launch with warps claiming 32-sample batches from a counter was tried:
+    //  4 % slower than letting the hardware schedule 128-thread CTAs)
+    const int64_t warp_base = (int64_t)blockIdx.x * SIM_THREADS + warp * 32;
     if (warp_base >= a.count) return;                       // warp-uniform
     const int nvalid = (int)min((int64_t)32, a.count - warp_base);
     const bool live = lane < nvalid;
@@ -554,8 +548,6 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
     }
     if (MODE == SIM_FOLD && lane == 0)
         atomicAdd(a.acc + 0, (unsigned long long)nvalid);  // header word 0: samples folded
-    if (!persist) return;
-  }
 }
 
 // Fold of an already materialised block of raw rows (the pilot matrix) into the accumulator
