@@ -209,14 +209,19 @@ def run_grid(args, vax, ctx, rank, world, local_rank, dist):
     boxes = grid_boxes(args.boxes)
     mine = list(range(rank, args.boxes, world))
 
+    box_args = [(boxes[b]["pro"], boxes[b]["anti"], boxes[b]["pressure"], boxes[b]["tau"], boxes[b]["nv0"],
+                 boxes[b]["nvmax"]) for b in mine]
+
     def one_pass(seed0):
-        checksum, ms = 0.0, 0.0
-        for b in mine:
-            cfg = nat.make_config(bounds_frac(boxes[b]), N_POP, T_DAYS, args.samples, seed0 + b, q_lo, q_hi)
-            out = ctx.run_bounds(cfg)
-            assert not out.c.aborted
-            checksum += float(out.mean[0][-1]); ms += out.c.device_ms
-        return checksum, ms
+        # the product's batched entry point: 2 host threads / contexts per GPU overlap one
+        # scenario's latency-bound pilot with the other's fold
+        res = vax.run_model_grid(box_args, ci, args.samples, N_POP, DATES, seeds=[seed0 + b for b in mine],
+                                 device=local_rank, workers=args.grid_workers)
+        checksum = 0.0
+        for r, err, msg in res:
+            assert err == ""
+            checksum += float(r["people_vaccinated_per_hundred"]["mean"][-1])
+        return checksum, 0.0
 
     for i in range(args.warmup):
         one_pass(10_000 * i)
@@ -246,7 +251,7 @@ def run_grid(args, vax, ctx, rank, world, local_rank, dist):
                                    "CI=%g, boxes partitioned over ranks" % (args.boxes, args.samples, ci),
                        "boxes": args.boxes, "samples_per_box": args.samples, "days": T_DAYS, "N": N_POP,
                        "generator": "bench.grid_boxes(seed=20261019)"},
-            "device_ms_per_step": float(t[1].item()) / args.steps, "gpu_launches": ctx.launch_count - l0,
+            "grid_workers": args.grid_workers, "gpu_launches_ctx0": ctx.launch_count - l0,
             "timing": "host wall clock around the whole grid incl. D2H of every box's bands (max over ranks)"}))
     if dist is not None:
         dist.destroy_process_group()
@@ -264,6 +269,7 @@ def main():
     ap.add_argument("--workload", default="usa", choices=["usa", "wide5y", "grid"],
                     help="usa: configs[1]/[2] (use --samples for 1e9/N); wide5y: configs[3]; grid: configs[4]")
     ap.add_argument("--boxes", type=int, default=1024, help="grid workload: number of bound boxes")
+    ap.add_argument("--grid-workers", type=int, default=2, help="grid workload: host threads/contexts per GPU")
     ap.add_argument("--ci", type=float, default=None, help="CI in percent (default 95; grid: 99)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

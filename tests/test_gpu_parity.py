@@ -516,3 +516,24 @@ def test_wide_5y_streamed_properties(vax, ctx):
     assert np.allclose(v["mean"] + s["mean"], r["mean"], rtol=1e-12)
     assert (np.diff(v["mean"]) >= 0).all()
     assert (v["upper"] <= 94.5 + 1e-9).all()       # 1 - min(anti) = 94.5 %
+
+
+def test_run_model_grid_equals_sequential_run_model(vax):
+    """configs[4] entry point: scenarios issued from 2 threads/contexts == one by one."""
+    import bench
+
+    boxes = bench.grid_boxes(6, seed=5)
+    args = [(b["pro"], b["anti"], b["pressure"], b["tau"], b["nv0"], b["nvmax"]) for b in boxes]
+    args.append(([70, 90], [50, 60], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10]))      # infeasible box
+    seeds = [100 + i for i in range(len(args))]
+    grid = vax.run_model_grid(args, 99, 150_000, 50000, USA_DATES, seeds=seeds, workers=2)
+    assert len(grid) == len(args)
+    for a, s_, g in zip(args, seeds, grid):
+        res, err, msg = vax.run_model(*a, 99, 150_000, 50000, USA_DATES, seed=s_)
+        assert (err, msg) == (g[1], g[2])
+        if res is None:
+            assert g[0] is None and err == ro.ERR_BOUNDS
+            continue
+        for k in SERIES:
+            for f in ("mean", "lower", "upper"):
+                assert np.array_equal(res[k][f], g[0][k][f]), (k, f)
