@@ -537,3 +537,29 @@ def test_run_model_grid_equals_sequential_run_model(vax):
         for k in SERIES:
             for f in ("mean", "lower", "upper"):
                 assert np.array_equal(res[k][f], g[0][k][f]), (k, f)
+
+
+def test_integration_md_stub_runs_and_matches(vax):
+    """The ctypes stub printed in INTEGRATION.md (what a reference maintainer would paste into
+    model.py) is executed verbatim and must reproduce run_model's arrays."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = [b for b in re.findall(r"```python\n(.*?)```", md, flags=re.S) if "run_sampling_bounds" in b][0]
+    cwd = os.getcwd()
+    os.chdir(root)
+    try:
+        ns = {}
+        exec(compile(code, "INTEGRATION.md", "exec"), ns)
+        data, res = ns["run_sampling_bounds"](usa_bounds_frac(), "2020-12-15", "2022-07-1", 0.95, 50000,
+                                              20000, 4711)
+    finally:
+        os.chdir(cwd)
+    ours, err, msg = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95, 20000,
+                                   50000, USA_DATES, seed=4711)
+    assert data["number_finished_samples"] == 20000 and err == ""
+    for k in SERIES:
+        for f in ("mean", "lower", "upper"):
+            assert np.array_equal(data[k][f], ours[k][f]), (k, f)
+        assert list(data[k]["dates"]) == list(ours[k]["dates"])
