@@ -66,7 +66,8 @@ struct Job {
     Win *d_wins = nullptr;
     unsigned long long *d_acc = nullptr;
     int64_t acc_words = 0, acc_cap = 0;
-    long long *d_tgt = nullptr, *d_res = nullptr;
+    int *d_tgt = nullptr;                 // [R][2][2] which wanted rank each window serves
+    long long *d_res = nullptr;
     // host state of the streaming job
     std::vector<Target> targets;          // [R][4]: lo_j, lo_j+1, hi_j, hi_j+1
     std::vector<WinPlan> plan;            // [R][2]
@@ -404,10 +405,14 @@ int plan_windows(vx_ctx *ctx, bool from_pilot)
     for (int64_t i = 0; i < R * 2; ++i) hw[i] = j->plan[i].w;
     { void *p_ = nullptr; int rc_;
       rc_ = pool_get(ctx, SLOT_WINS, sizeof(Win) * R * 2, &p_); if (rc_) return rc_; j->d_wins = (Win *)p_;
-      rc_ = pool_get(ctx, SLOT_TGT, sizeof(long long) * R * 4, &p_); if (rc_) return rc_; j->d_tgt = (long long *)p_;
+      rc_ = pool_get(ctx, SLOT_TGT, sizeof(int) * R * 4, &p_); if (rc_) return rc_; j->d_tgt = (int *)p_;
       rc_ = pool_get(ctx, SLOT_RES, sizeof(long long) * R * 4, &p_); if (rc_) return rc_; j->d_res = (long long *)p_; }
+    std::vector<int> hk(R * 4);
+    for (int64_t i = 0; i < R * 2; ++i)
+        for (int k = 0; k < 2; ++k) hk[i * 2 + k] = j->plan[i].tgt[k];
+    // pageable sources: the async copies return once the data is staged, the vectors may go
     CK(cudaMemcpyAsync(j->d_wins, hw.data(), sizeof(Win) * R * 2, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(j->d_tgt, hk.data(), sizeof(int) * R * 4, cudaMemcpyHostToDevice, ctx->stream));
     return VX_OK;
 }
 
@@ -630,12 +635,10 @@ void vx_host_quantile_index(int64_t n, double q, int64_t *prev, int64_t *next, d
 {
     // method="linear": virtual index (n-1)*q; _get_indexes + _get_gamma
     const double vi = (double)(n - 1) * q;
-    double p = std::floor(vi);
-    int64_t pi = (int64_t)p, ni = pi + 1;
-    if (vi >= (double)(n - 1)) { pi = n - 1; ni = n - 1; }
-    if (vi < 0) { pi = 0; ni = 0; }
+    long long pi, ni;
+    quantile_ranks((long long)n, q, pi, ni);
     *prev = pi; *next = ni;
-    *gamma = vi - p;
+    *gamma = vi - std::floor(vi);
 }
 
 double vx_host_count_to_value(int series, int64_t count, int64_t N)
@@ -917,6 +920,13 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     if (!j->finished) {
         const int64_t R = j->R;
         unsigned long long hdr[ACC_HDR];
+        const int64_t warps = 2 * R, grid = (warps * 32 + 255) / 256;
+        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R, j->cfg.q_lo, j->cfg.q_hi);
+        CKL();
+        std::vector<long long> hres(R * 4);
+        std::vector<long long> sums(R);
+        CK(cudaMemcpyAsync(hres.data(), j->d_res, sizeof(long long) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(sums.data(), j->d_acc + ACC_HDR, sizeof(long long) * R, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(hdr, j->d_acc, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         const int64_t n = (int64_t)hdr[0];
@@ -924,7 +934,7 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
         if (!j->ranks_set) {
             j->n_total = n;
             int64_t p0, n0, p1, n1; double g;
-            vx_host_quantile_index(n, j->cfg.q_lo, &p0, &n0, &g);
+            vx_host_quantile_index(n, j->cfg.q_lo, &p0, &n0, &g);      // what the kernel derived from acc[0]
             vx_host_quantile_index(n, j->cfg.q_hi, &p1, &n1, &g);
             for (int64_t r = 0; r < R; ++r) {
                 Target *t = &j->targets[r * 4];
@@ -934,21 +944,6 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
         } else if (n != j->n_total) {
             return fail(ctx, VX_ERR_STATE, "pass folded %lld samples, first pass folded %lld", (long long)n, (long long)j->n_total);
         }
-        std::vector<long long> ht(R * 4);
-        for (int64_t i = 0; i < R * 2; ++i)
-            for (int k = 0; k < 2; ++k) {
-                const int ti = j->plan[i].tgt[k];
-                ht[i * 2 + k] = ti < 0 ? -1 : j->targets[(i / 2) * 4 + ti].rank;
-            }
-        CK(cudaMemcpyAsync(j->d_tgt, ht.data(), sizeof(long long) * R * 4, cudaMemcpyHostToDevice, ctx->stream));
-        const int64_t warps = 2 * R, grid = (warps * 32 + 255) / 256;
-        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R);
-        CKL();
-        std::vector<long long> hres(R * 4);
-        std::vector<long long> sums(R);
-        CK(cudaMemcpyAsync(hres.data(), j->d_res, sizeof(long long) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(sums.data(), j->d_acc + ACC_HDR, sizeof(long long) * R, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
         bool all = true;
         for (int64_t i = 0; i < R * 2; ++i) {
             const WinPlan &wp = j->plan[i];

@@ -797,13 +797,27 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
 }
 
 // --------------------------------------------- order statistics out of merged windows
-// One warp per (row, window).  tgt[(row*2+w)*2 + {0,1}] = global ranks served by the window
-// (-1: none).  res gets, per target, (status << 32) | bin with status 0 found, 1 the rank
-// lies below the window (rank < #values < a), 2 above it.
+// np.quantile(method="linear"): virtual index (n-1)*q -> the two neighbouring ranks
+// (numpy/lib/_function_base_impl.py: _get_indexes).  Same arithmetic on host and device.
+__host__ __device__ inline void quantile_ranks(long long n, double q, long long &prev, long long &next)
+{
+    const double vi = (double)(n - 1) * q;
+    const double p = floor(vi);
+    prev = (long long)p; next = prev + 1;
+    if (vi >= (double)(n - 1)) { prev = n - 1; next = n - 1; }
+    if (vi < 0) { prev = 0; next = 0; }
+}
+
+// One warp per (row, window).  kind[(row*2+w)*2 + {0,1}] says which of the row's four wanted
+// order statistics the window serves (0: lower band rank j, 1: j+1, 2: upper band rank j, 3: j+1;
+// -1: none); the ranks themselves follow from n = acc[0] (samples folded by all ranks) on the
+// device.  res gets, per target, (status << 32) | bin with status 0 found, 1 the rank lies
+// below the window (rank < #values < a), 2 above it.
 __global__ void __launch_bounds__(256) vx_extract_kernel(const unsigned long long *__restrict__ acc,
                                                          const Win *__restrict__ wins,
-                                                         const long long *__restrict__ tgt,
-                                                         long long *__restrict__ res, int R)
+                                                         const int *__restrict__ kind,
+                                                         long long *__restrict__ res, int R,
+                                                         double q_lo, double q_hi)
 {
     const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (gw >= 2 * R) return;
@@ -811,24 +825,41 @@ __global__ void __launch_bounds__(256) vx_extract_kernel(const unsigned long lon
     const uint32_t nb = w.len >> w.shift;
     const unsigned long long *hist = acc + ACC_HDR + 3 * (int64_t)R + w.off;
     const long long below = (long long)acc[ACC_HDR + R + gw];
-    long long t[2] = {tgt[gw * 2], tgt[gw * 2 + 1]};
-    long long r[2] = {-1, -1};
-    for (int k = 0; k < 2; ++k)
+    long long rk[4];
+    quantile_ranks((long long)acc[0], q_lo, rk[0], rk[1]);
+    quantile_ranks((long long)acc[0], q_hi, rk[2], rk[3]);
+    long long t[2], r[2] = {-1, -1};
+    for (int k = 0; k < 2; ++k) {
+        const int kd = kind[gw * 2 + k];
+        t[k] = kd < 0 ? -1 : (kd == 0 ? rk[0] : kd == 1 ? rk[1] : kd == 2 ? rk[2] : rk[3]);
         if (t[k] >= 0 && t[k] < below) { r[k] = (1ll << 32); t[k] = -1; }
+    }
     long long cum = below;
-    for (uint32_t b0 = 0; b0 < nb && (t[0] >= 0 || t[1] >= 0); b0 += 32) {
-        const uint32_t b = b0 + lane;
-        long long h = (b < nb) ? (long long)hist[b] : 0;
-        long long inc = h;                                   // inclusive warp scan
+    for (uint32_t b0 = 0; b0 < nb && (t[0] >= 0 || t[1] >= 0); b0 += 128) {
+        const uint32_t b = b0 + 4 * lane;                    // 4 bins per lane: 4 loads in flight
+        const long long h0 = (b < nb) ? (long long)hist[b] : 0;
+        const long long h1 = (b + 1 < nb) ? (long long)hist[b + 1] : 0;
+        const long long h2 = (b + 2 < nb) ? (long long)hist[b + 2] : 0;
+        const long long h3 = (b + 3 < nb) ? (long long)hist[b + 3] : 0;
+        const long long lsum = h0 + h1 + h2 + h3;
+        long long incl = lsum;                                // inclusive warp scan
         for (int o = 1; o < 32; o <<= 1) {
-            const long long y = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += y;
+            const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
         }
-        const long long c_incl = cum + inc;
+        const long long c_excl = cum + incl - lsum, c_incl = cum + incl;
         for (int k = 0; k < 2; ++k) {
             if (t[k] < 0) continue;
             const uint32_t m = __ballot_sync(0xffffffffu, t[k] < c_incl);
-            if (m) { r[k] = (long long)(b0 + (uint32_t)(__ffs(m) - 1)); t[k] = -1; }
+            if (m) {
+                long long c = c_excl;
+                int i = 3;
+                if (t[k] < c + h0) i = 0;
+                else if (t[k] < c + h0 + h1) i = 1;
+                else if (t[k] < c + h0 + h1 + h2) i = 2;
+                r[k] = (long long)__shfl_sync(0xffffffffu, (int)(b + i), __ffs(m) - 1);
+                t[k] = -1;
+            }
         }
         cum = __shfl_sync(0xffffffffu, c_incl, 31);
     }
