@@ -102,7 +102,7 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -261,7 +261,7 @@ def run_grid(args, vax, ctx, rank, world, local_rank, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--samples", type=int, default=1_000_000, help="samples per GPU per step")
