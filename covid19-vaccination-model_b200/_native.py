@@ -22,6 +22,7 @@ SERIES = (
 VX_OK, VX_REFINE = 0, 1
 VX_ERR_NODEVICE = -5
 MODE_STOCHASTIC, MODE_EXPECTED = 0, 1
+DIRECT_MAX_DEFAULT = 131072   # vx_config.direct_max == 0 (csrc/vaxmc.cu: job_begin_common)
 
 
 class VaxmcError(RuntimeError):

@@ -36,6 +36,10 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// fixed-point scale of the p_soft_no moments when they travel in the int64 slab: sums of up
+// to 8e9 samples of values in [0,1] stay below 2^63, the mean keeps 9 digits
+constexpr double STATS_FIX = 1073741824.0;   // 2^30
+
 struct Target {
     int64_t rank = 0;
     int64_t lo = 0, hi = 0; // the order statistic is known to lie in [lo, hi]
@@ -56,7 +60,9 @@ struct Job {
     bool explicit_params = false;
     bool direct = false;
     bool stats_set = false, piloted = false, aborted = false, finished = false;
-    double gstats[4] = {0, 0, 0, 0};
+    double gstats[4] = {0, 0, 0, 0};      // global: rejections, sum s, sum s^2, samples
+    double lstats[4] = {0, 0, 0, 0};      // this shard's (vx_job_param_stats)
+    bool lstats_set = false, stats_in_slab = false;
     int64_t n_pilot = 0;
     int64_t vmax[4] = {0, 0, 0, 0};       // per raw-row class: n_vacc, dose, received, stock
     // device buffers
@@ -711,6 +717,7 @@ int vx_job_param_stats(vx_ctx *ctx, double stats[4])
     Phase ph_(ctx, "param_stats");
     stats[0] = stats[1] = stats[2] = 0.0;
     stats[3] = (double)j->shard_count;
+    struct Keep { Job *j; double *s; ~Keep() { memcpy(j->lstats, s, sizeof j->lstats); j->lstats_set = true; } } keep_{j, stats};
     if (j->explicit_params || j->shard_count == 0) return VX_OK;
     const double *b = j->cfg.bounds;
     if (std::min(b[0], b[1]) + std::min(b[2], b[3]) > 1.0) {
@@ -850,13 +857,23 @@ int vx_job_accumulate(vx_ctx *ctx)
     if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
     Job *j = ctx->job;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_accumulate");
-    if (!j->stats_set) return fail(ctx, VX_ERR_STATE, "vx_job_set_param_stats must precede vx_job_accumulate");
+    if (!j->stats_set && !j->lstats_set)
+        return fail(ctx, VX_ERR_STATE, "vx_job_param_stats (or vx_job_set_param_stats) must precede vx_job_accumulate");
     if (j->aborted) return fail(ctx, VX_ERR_STATE, "job aborted by the rejection rule");
     if (j->direct || j->finished) return VX_OK;
     int rc = need_device(ctx);
     if (rc) return rc;
     Phase ph_(ctx, "accumulate (fold)");
     CK(cudaMemsetAsync(j->d_acc, 0, sizeof(unsigned long long) * j->acc_words, ctx->stream));
+    if (!j->stats_set) {
+        // no separate statistics collective: this shard's rejection count and fixed-point moments
+        // of p_soft_no ride in header words 2..5 of the slab the ranks all-reduce anyway
+        j->stats_in_slab = true;
+        const unsigned long long hs[4] = {
+            (unsigned long long)j->lstats[0], (unsigned long long)std::llround(j->lstats[1] * STATS_FIX),
+            (unsigned long long)std::llround(j->lstats[2] * STATS_FIX), (unsigned long long)j->lstats[3]};
+        CK(cudaMemcpyAsync(j->d_acc + 2, hs, sizeof hs, cudaMemcpyHostToDevice, ctx->stream));
+    }
     const bool first_pass = j->n_passes == 0;
     const int64_t todo = first_pass ? j->shard_count : j->shard_done;
     const bool timed = first_pass && j->cfg.max_running_time > 0.0;
@@ -915,7 +932,13 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     int rc = need_device(ctx);
     if (rc) return rc;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_finalize");
-    if (!j->stats_set) return fail(ctx, VX_ERR_STATE, "vx_job_set_param_stats must precede vx_job_finalize");
+    if (!j->stats_set && !j->lstats_set)
+        return fail(ctx, VX_ERR_STATE, "vx_job_param_stats (or vx_job_set_param_stats) must precede vx_job_finalize");
+    if (!j->stats_set && j->direct) {       // a direct job without a statistics collective: local == global
+        memcpy(j->gstats, j->lstats, sizeof j->gstats);
+        j->stats_set = true;
+        j->aborted = j->gstats[0] > 10.0 * (double)j->cfg.n_samples;
+    }
     Phase ph_(ctx, "finalize");
     if (!j->finished) {
         const int64_t R = j->R;
@@ -931,6 +954,17 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
         CK(cudaStreamSynchronize(ctx->stream));
         const int64_t n = (int64_t)hdr[0];
         if (n < 1) return fail(ctx, VX_ERR_STATE, "no samples were folded");
+        if (j->stats_in_slab) {
+            j->gstats[0] = (double)hdr[2]; j->gstats[1] = (double)hdr[3] / STATS_FIX;
+            j->gstats[2] = (double)hdr[4] / STATS_FIX; j->gstats[3] = (double)hdr[5];
+            j->aborted = j->gstats[0] > 10.0 * (double)j->cfg.n_samples;      // model.py:282-287
+            if (j->aborted) {
+                res->device_ms = res->fold_ms = res->pilot_ms = 0; res->fold_launches = 0;
+                j->n_total = 0;
+                fill_result_scalars(ctx, res);
+                return VX_OK;
+            }
+        }
         if (!j->ranks_set) {
             j->n_total = n;
             int64_t p0, n0, p1, n1; double g;

@@ -85,46 +85,63 @@ class ContextEngine:
 
 
 def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out, all_reduce_async=None):
-    """Drive one rank of a sharded job.
+    """Drive one rank of a sharded job.  `all_reduce(tensor)` sums in place across ranks and
+    returns when the result is usable.
 
-    `all_reduce(tensor)` sums in place across ranks and returns when the result is usable;
-    `all_reduce_async(tensor)` (optional) starts the same reduction and returns a callable that
-    waits for it -- used to hide the small statistics reduction behind the replicated pilot.
+    One collective per pass: the shard's parameter statistics (rejections, moments of
+    p_soft_no) ride in the header of the int64 slab.  A direct job (n <= direct_max) is computed
+    whole on every rank and needs no collective at all.
     """
-    first, count = shard_range(cfg.n_samples, rank, world)
+    direct = cfg.n_samples <= (cfg.direct_max if cfg.direct_max > 0 else nat.DIRECT_MAX_DEFAULT) \
+        or cfg.mode == nat.MODE_EXPECTED
+    first, count = (0, cfg.n_samples) if direct else shard_range(cfg.n_samples, rank, world)
+    trace = _Trace(rank)
     engine.begin(cfg, first, count)
+    trace("begin")
     try:
-        t = engine.stats_tensor(engine.param_stats())
-        wait = all_reduce_async(t) if all_reduce_async is not None else None
-        if wait is None:
-            all_reduce(t)
+        st = engine.param_stats()
+        trace("param_stats")
         out = make_out()
-        if wait is None:
-            st = t.cpu().numpy().astype(np.float64)
-            if engine.set_param_stats(st):
-                out.c.aborted = 1
-                out.c.n_rejected = int(st[0])
-                return out
-            engine.pilot()
-        else:
-            engine.pilot()          # replicated work, overlaps the statistics reduction
-            wait()
-            st = t.cpu().numpy().astype(np.float64)
-            if engine.set_param_stats(st):
-                out.c.aborted = 1
-                out.c.n_rejected = int(st[0])
-                return out
+        if st[0] > 10.0 * cfg.n_samples:          # this shard alone already breaks the 10*n_rep rule
+            out.c.aborted = 1
+            out.c.n_rejected = int(st[0])
+            return out
+        engine.pilot()
+        trace("pilot")
         for _ in range(64):
             engine.accumulate()
+            trace("accumulate")
             acc = engine.acc_tensor()
             if acc is not None:
                 all_reduce(acc)
+            trace("acc all-reduce")
             rc = engine.finalize(out)
+            trace("finalize")
             if rc != nat.VX_REFINE:
                 return out
         raise RuntimeError("window refinement did not converge")
     finally:
         engine.end()
+
+
+class _Trace:
+    """VX_TRACE=1: wall time of each stage of run_sharded on rank 0 (stderr)."""
+
+    def __init__(self, rank):
+        self.on = rank == 0 and bool(os.environ.get("VX_TRACE"))
+        if self.on:
+            import time
+
+            self.clock = time.perf_counter
+            self.t = self.clock()
+
+    def __call__(self, what):
+        if self.on:
+            import sys
+
+            now = self.clock()
+            print(f"[vx trace py] {what:24s} {1e3 * (now - self.t):8.3f} ms", file=sys.stderr)
+            self.t = now
 
 
 def make_torch_reducers(dist, device):

@@ -136,11 +136,13 @@ int vx_expected_series(vx_ctx *ctx, const vx_config *cfg, const double *params, 
 
 /* ---- staged job: one shard of the global sample range per GPU (multi-GPU path) ----
  *   vx_job_begin(cfg, shard_first, shard_count)
- *   vx_job_param_stats(stats[4])        -> all-reduce(sum) stats across ranks (float64);
- *   vx_job_pilot()                      replicated on every rank (same global sample ids);
- *                                       may run while the stats all-reduce is in flight
- *   vx_job_set_param_stats(stats[4])    <- the reduced values; returns 1 = aborted (then
- *                                       skip to vx_job_end)
+ *   vx_job_param_stats(stats[4])        this shard's rejection count / p_soft_no moments
+ *   [vx_job_set_param_stats(stats[4])]  OPTIONAL: hand back stats summed over ranks by the
+ *                                       caller (returns 1 = aborted, then skip to vx_job_end).
+ *                                       Without it the shard's statistics travel in the header
+ *                                       of the slab (fixed point) and are merged by the same
+ *                                       all-reduce; vx_job_finalize then reports `aborted`.
+ *   vx_job_pilot()                      replicated on every rank (same global sample ids)
  *   loop: vx_job_accumulate()           streaming fold of this rank's shard
  *         vx_job_acc(&dev_ptr,&n_words) -> all-reduce(sum) this int64 device slab (NCCL)
  *         vx_job_finalize(res)          VX_OK: done;  VX_REFINE: loop again

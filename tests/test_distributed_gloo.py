@@ -3,9 +3,9 @@
 The arithmetic of a rank lives in libvaxmc.so and needs a GPU; here a FakeEngine with the
 same interface folds a deterministic integer function of the GLOBAL sample id, which is
 enough to pin what the driver is responsible for: disjoint contiguous shards that cover the
-range, the float64 all-reduce of the parameter statistics, the int64 all-reduce of the
-accumulator slab once per pass, the VX_REFINE loop, the abort path -- and that the merged
-integers do not depend on the number of ranks.
+range, ONE int64 all-reduce of the accumulator slab per pass (the shard's parameter statistics
+ride in its header), the VX_REFINE loop, the abort path decided on the merged rejection count
+-- and that the merged integers do not depend on the number of ranks.
 """
 import importlib
 import os
@@ -37,7 +37,8 @@ class _Out:
 
 
 class FakeEngine:
-    """Integer fold of f(id) = (id * 2654435761) % 1009 over the shard, two passes."""
+    """Integer fold of f(id) = (id * 2654435761) % 1009 over the shard, two passes; the shard's
+    rejection count rides in word 2 of the slab, as in libvaxmc."""
 
     def __init__(self, infeasible=False):
         self.infeasible = infeasible
@@ -50,16 +51,9 @@ class FakeEngine:
 
     def param_stats(self):
         ids = np.arange(self.first, self.first + self.count, dtype=np.int64)
-        rej = float((ids % 3 == 0).sum()) if not self.infeasible else 11.0 * self.count
+        self.rej = int((ids % 3 == 0).sum()) if not self.infeasible else 11 * self.count
         s = (ids % 100) / 100.0
-        return np.array([rej, s.sum(), (s * s).sum(), float(self.count)])
-
-    def stats_tensor(self, st):
-        return torch.from_numpy(np.ascontiguousarray(st))
-
-    def set_param_stats(self, st):
-        self.gstats = np.array(st)
-        return st[0] > 10.0 * self.n
+        return np.array([float(self.rej), s.sum(), (s * s).sum(), float(self.count)])
 
     def pilot(self):
         self.calls.append(("pilot",))
@@ -68,7 +62,7 @@ class FakeEngine:
         ids = np.arange(self.first, self.first + self.count, dtype=np.uint64)
         f = (ids * np.uint64(2654435761)) % np.uint64(1009)
         hist = np.bincount(f.astype(np.int64), minlength=1009)
-        self.acc = torch.from_numpy(np.concatenate([[self.count, int(f.sum())], hist]).astype(np.int64))
+        self.acc = torch.from_numpy(np.concatenate([[self.count, int(f.sum()), self.rej], hist]).astype(np.int64))
         self.passes += 1
 
     def acc_tensor(self):
@@ -77,6 +71,9 @@ class FakeEngine:
     def finalize(self, out):
         out.merged = self.acc.clone().numpy()
         out.c.n_finished = int(out.merged[0])
+        if out.merged[2] > 10 * self.n:              # model.py:282-287 on the MERGED count
+            out.c.aborted = 1
+            return 0
         return 1 if self.passes < 2 else 0          # VX_REFINE once, then VX_OK
 
     def end(self):
@@ -87,6 +84,8 @@ class _Cfg:
     def __init__(self, n):
         self.n_samples = n
         self.T = 10
+        self.direct_max = 1          # always streamed
+        self.mode = 0
 
 
 def _worker(rank, world, port, n, q):
@@ -104,13 +103,8 @@ def _worker(rank, world, port, n, q):
 
         out = d.run_sharded(eng, _Cfg(n), rank, world, all_reduce, _Out)
         bad = FakeEngine(infeasible=True)
-        _, all_reduce_async = d.make_torch_reducers(dist, None)
-        out_bad = d.run_sharded(bad, _Cfg(n), rank, world, all_reduce, _Out, all_reduce_async)
-        eng2 = FakeEngine()
-        out2 = d.run_sharded(eng2, _Cfg(n), rank, world, all_reduce, _Out, all_reduce_async)
-        assert np.array_equal(out2.merged, out.merged) and eng2.calls[1] == ("pilot",)
-        q.put((rank, out.merged.tolist(), eng.gstats.tolist(), eng.passes, n_reduces[0], eng.calls,
-               out_bad.c.aborted, bad.passes))
+        out_bad = d.run_sharded(bad, _Cfg(n), rank, world, all_reduce, _Out)
+        q.put((rank, out.merged.tolist(), eng.passes, n_reduces[0], eng.calls, out_bad.c.aborted, bad.passes))
     finally:
         dist.destroy_process_group()
 
@@ -127,10 +121,8 @@ def _expected(n):
     ids = np.arange(n, dtype=np.uint64)
     f = (ids * np.uint64(2654435761)) % np.uint64(1009)
     hist = np.bincount(f.astype(np.int64), minlength=1009)
-    merged = np.concatenate([[n, int(f.sum())], hist]).astype(np.int64)
-    idl = np.arange(n)
-    s = (idl % 100) / 100.0
-    return merged, np.array([float((idl % 3 == 0).sum()), s.sum(), (s * s).sum(), float(n)])
+    rej = int((np.arange(n) % 3 == 0).sum())
+    return np.concatenate([[n, int(f.sum()), rej], hist]).astype(np.int64)
 
 
 @pytest.mark.parametrize("n", [1001, 64])
@@ -146,14 +138,14 @@ def test_two_rank_gloo_merge_equals_single_rank(n):
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    merged, stats = _expected(n)
-    for rank, m, st, passes, n_red, calls, aborted, bad_passes in res:
+    merged = _expected(n)
+    for rank, m, passes, n_red, calls, aborted, bad_passes in res:
         assert np.array_equal(np.array(m), merged)              # integer merge is exact
-        assert np.allclose(st, stats, rtol=1e-14)
         assert passes == 2                                       # one VX_REFINE round trip
-        assert n_red == 1 + 2 + 2                                # stats + one per pass, twice (async stats not counted)
+        assert n_red == 2 + 1                                    # ONE collective per pass (+1: the aborting job)
         assert calls[0][0] == "begin" and calls[1] == ("pilot",) and calls[-1] == ("end",)
-        assert aborted == 1 and bad_passes == 0                  # abort path: no pass is run
+        # neither shard alone breaks the 10*n rule (11*n/2 each); the merged count does
+        assert aborted == 1 and bad_passes == 1
 
 
 def test_shard_range_partitions_exactly():
@@ -174,5 +166,4 @@ def test_single_process_driver_equals_sharded_sum():
     d = importlib.import_module(PKG + ".distributed")
     eng = FakeEngine()
     out = d.run_sharded(eng, _Cfg(1001), 0, 1, lambda t: None, _Out)
-    merged, _ = _expected(1001)
-    assert np.array_equal(out.merged, merged)
+    assert np.array_equal(out.merged, _expected(1001))

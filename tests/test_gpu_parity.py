@@ -432,22 +432,23 @@ def test_sharding_is_bit_exact(vax, ctx):
     n = 40000
     cfg = _cfg(vax, bounds, n, seed=2025, direct_max=1, pilot_samples=4096)
     single = ctx.run_bounds(cfg)
-    for world in (2, 3, 8):
+    for world, stats_in_slab in ((2, False), (3, True), (8, True)):
         ctxs = [nat.Context(0) for _ in range(world)]
         engines = [dist.ContextEngine(c) for c in ctxs]
         for r, e in enumerate(engines):
             e.begin(cfg, *dist.shard_range(n, r, world))
-        st = sum(e.param_stats() for e in engines)
-        assert st[3] == n
+        sts = [e.param_stats() for e in engines]
+        assert sum(sts)[3] == n
         for e in engines:
-            assert not e.set_param_stats(st)
+            if not stats_in_slab:                      # caller-side reduction of the statistics
+                assert not e.ctx.job_set_param_stats(sum(sts))
             e.pilot()
         outs = [nat.ResultBuffers(cfg.T) for _ in engines]
         for _ in range(8):
             for e in engines:
                 e.accumulate()
             accs = [e.acc_tensor() for e in engines]
-            total = torch.stack(accs).sum(dim=0)
+            total = torch.stack(accs).sum(dim=0)       # what the NCCL all-reduce(sum) does
             for a in accs:
                 a.copy_(total)
             torch.cuda.synchronize()
@@ -457,12 +458,34 @@ def test_sharding_is_bit_exact(vax, ctx):
                 break
         for o in outs:
             assert _same(single, o)
-            assert o.c.n_rejected == single.c.n_rejected
-            assert o.c.soft_no_mean == pytest.approx(single.c.soft_no_mean, rel=1e-13)
+            assert o.c.n_rejected == single.c.n_rejected and not o.c.aborted
+            assert o.c.soft_no_mean == pytest.approx(single.c.soft_no_mean, rel=1e-8)
+            assert o.c.soft_no_std == pytest.approx(single.c.soft_no_std, rel=1e-6)
         for e in engines:
             e.end()
         for c in ctxs:
             c.close()
+    # infeasible bounds discovered through the slab header: every rank reports `aborted`
+    bad = _cfg(vax, np.array([0.7, 0.9, 0.5, 0.6, 0, 0.1, 3, 4, 0.002, 0.0024, 0.1, 0.1]), n, seed=3,
+               direct_max=1, pilot_samples=4096)
+    ctxs = [nat.Context(0) for _ in range(2)]
+    engines = [dist.ContextEngine(c) for c in ctxs]
+    outs = [nat.ResultBuffers(bad.T) for _ in engines]
+    for r, e in enumerate(engines):
+        e.begin(bad, *dist.shard_range(n, r, 2))
+        e.param_stats()
+        e.pilot()
+        e.accumulate()
+    accs = [e.acc_tensor() for e in engines]
+    total = torch.stack(accs).sum(dim=0)
+    for a in accs:
+        a.copy_(total)
+    torch.cuda.synchronize()
+    for e, o in zip(engines, outs):
+        assert e.finalize(o) == nat.VX_OK and o.c.aborted == 1 and o.c.n_rejected > 10 * n
+        e.end()
+    for c in ctxs:
+        c.close()
 
 
 def test_max_running_time_partial_results(vax, ctx):
