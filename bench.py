@@ -271,6 +271,8 @@ def main():
     ap.add_argument("--boxes", type=int, default=1024, help="grid workload: number of bound boxes")
     ap.add_argument("--grid-workers", type=int, default=2, help="grid workload: host threads/contexts per GPU")
     ap.add_argument("--ci", type=float, default=None, help="CI in percent (default 95; grid: 99)")
+    ap.add_argument("--direct", action="store_true",
+                    help="force the materialise + radix-select path (HBM-bound passes) instead of the streaming fold")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -325,7 +327,8 @@ def main():
     all_reduce, all_reduce_async = dmod.make_torch_reducers(dist, local_rank) if dist else (None, None)
 
     def one_job(seed):
-        cfg = nat.make_config(bounds, N_POP, T_DAYS, n_global, seed, q_lo, q_hi)
+        cfg = nat.make_config(bounds, N_POP, T_DAYS, n_global, seed, q_lo, q_hi,
+                              direct_max=(n_global + 1) if args.direct else 0)
         if world == 1:
             return ctx.run_bounds(cfg)
         return dmod.run_sharded(dmod.ContextEngine(ctx), cfg, rank, world, all_reduce,
@@ -371,7 +374,8 @@ def main():
             t0 = time.perf_counter()
             res, err, msg = vax.run_model(wl_bounds["pro"], wl_bounds["anti"], wl_bounds["pressure"],
                                           wl_bounds["tau"], wl_bounds["nv0"], wl_bounds["nvmax"], CI_PCT,
-                                          n_global, N_POP, wl_dates, seed=3000 + i)
+                                          n_global, N_POP, wl_dates, seed=3000 + i,
+                                          direct_max=(n_global + 1) if args.direct else 0)
             checksum = float(res["people_vaccinated_per_hundred"]["mean"][-1])  # host read of the result
             dt = time.perf_counter() - t0
             assert err == "" and checksum > 0

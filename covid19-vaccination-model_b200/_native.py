@@ -107,6 +107,7 @@ SYMBOLS = {
     "vx_test_normal": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.POINTER(C.c_float)]),
     "vx_test_select": (C.c_int, [_vp, _i32p, C.c_int64, C.c_int64, _i64p, C.c_int32, _i32p, _i64p]),
     "vx_launch_count": (C.c_int64, [_vp]),
+    "vx_select_fallbacks": (C.c_int64, [_vp]),
 }
 
 _LIB = None
@@ -218,6 +219,10 @@ class Context:
 
     def trim(self):
         self._ck(self._lib.vx_trim(self._h))
+
+    @property
+    def select_fallbacks(self) -> int:
+        return int(self._lib.vx_select_fallbacks(self._h))
 
     @property
     def launch_count(self) -> int:

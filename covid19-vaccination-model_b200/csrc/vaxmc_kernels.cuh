@@ -676,30 +676,118 @@ template <> struct KeyTraits<double> {
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_MAXR = 8;
 
+template <typename T> struct SelScratch {
+    typedef typename KeyTraits<T>::key_t key_t;
+    uint32_t hist[SEL_MAXR][256];
+    key_t prefix[SEL_MAXR], dprefix[SEL_MAXR];
+    long long rem[SEL_MAXR];
+    int hid[SEL_MAXR];
+    int ndist;
+};
+
+// MSD radix select of `nranks` order statistics of src[0..n) (global or shared memory) by the
+// whole CTA.  In: S.rem[k] = rank k; first_key / diff = any key of the data and the OR of
+// (key ^ first_key) over the data (bits that vary).  Out: S.prefix[k] = key of the order
+// statistic.  Ends with a __syncthreads().
 template <typename T>
-__global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
-    const T *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks,
-    int nranks, T *__restrict__ out /*[rows][nranks]*/,
-    typename KeyTraits<T>::sum_t *__restrict__ sums /*[rows]*/)
+__device__ void block_radix_select(const T *__restrict__ src, int64_t n, int nranks, SelScratch<T> &S,
+                                   typename KeyTraits<T>::key_t first_key,
+                                   typename KeyTraits<T>::key_t diff)
 {
     typedef KeyTraits<T> KT;
     typedef typename KT::key_t key_t;
-    typedef typename KT::sum_t sum_t;
-    __shared__ uint32_t hist[SEL_MAXR][256];
-    __shared__ key_t prefix[SEL_MAXR], dprefix[SEL_MAXR];
-    __shared__ long long rem[SEL_MAXR];
-    __shared__ int hid[SEL_MAXR];
-    __shared__ int ndist;
-    __shared__ sum_t red_sum[SEL_THREADS];
-    __shared__ key_t red_xor[SEL_THREADS];
-
-    const T *row = data + (int64_t)blockIdx.x * ld;
     const int tid = threadIdx.x;
+    // keys agree above bit `top`: those bits go straight into the prefix
+    int top = 0;
+    if (diff) top = (KT::BITS == 64) ? 64 - __clzll((long long)diff) : 32 - __clz((int)(uint32_t)diff);
+    const int npass = (top + 7) / 8;
+    if (tid < nranks) S.prefix[tid] = (npass * 8 >= KT::BITS) ? (key_t)0 : (first_key >> (npass * 8));
+    __syncthreads();
 
-    // pass 0: row sum (fixed-order tree -> deterministic) and the bits that vary in the row
-    sum_t acc = 0;
-    key_t diff = 0;
-    const key_t first_key = KT::to_key(row[0]);
+    for (int pass = npass - 1; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        if (tid == 0) {
+            int nd = 0;
+            for (int k = 0; k < nranks; ++k) {
+                int f = -1;
+                for (int d = 0; d < nd; ++d) if (S.dprefix[d] == S.prefix[k]) { f = d; break; }
+                if (f < 0) { f = nd; S.dprefix[nd++] = S.prefix[k]; }
+                S.hid[k] = f;
+            }
+            S.ndist = nd;
+        }
+        for (int i = tid; i < SEL_MAXR * 256; i += SEL_THREADS) (&S.hist[0][0])[i] = 0;
+        __syncthreads();
+        const int nd = S.ndist;
+        const bool whole = (shift + 8 >= KT::BITS);
+        for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+            const int64_t i = i0 + tid;
+            const bool in = i < n;
+            key_t key = 0, hi = 0;
+            uint32_t bin = 0;
+            if (in) {
+                key = KT::to_key(src[i]);
+                hi = whole ? (key_t)0 : (key >> (shift + 8));
+                bin = (uint32_t)(key >> shift) & 255u;
+            }
+            for (int d = 0; d < nd; ++d) {
+                const bool hit = in && (hi == S.dprefix[d]);
+                // warp-aggregate the common all-lanes-same-bin case (flat rows)
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m == 0) continue;
+                const int leader = __ffs(m) - 1;
+                const uint32_t lbin = __shfl_sync(0xffffffffu, bin, leader);
+                const uint32_t same = __ballot_sync(0xffffffffu, hit && bin == lbin);
+                if (same == m) {
+                    if ((tid & 31) == leader) atomicAdd(&S.hist[d][lbin], (uint32_t)__popc(m));
+                } else if (hit) {
+                    atomicAdd(&S.hist[d][bin], 1u);
+                }
+            }
+        }
+        __syncthreads();
+        if ((tid >> 5) < nranks) {           // warp w locates rank w in its 256-bin histogram
+            const int w = tid >> 5, l = tid & 31;
+            const uint32_t *h = S.hist[S.hid[w]] + 8 * l;
+            uint32_t c[8], lsum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = h[i]; lsum += c[i]; }
+            long long incl = lsum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (l >= o) incl += y;
+            }
+            const long long excl = incl - lsum, r = S.rem[w];
+            const uint32_t m = __ballot_sync(0xffffffffu, r >= excl && r < incl);
+            const int src_lane = m ? __ffs(m) - 1 : 31;
+            if (l == src_lane) {
+                long long cum = excl;
+                int i = 0;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    if (i == q && r >= cum + (long long)c[q]) { cum += c[q]; i = q + 1; }
+                }
+                S.rem[w] = r - cum;
+                S.prefix[w] = (S.prefix[w] << 8) | (key_t)(8 * l + i);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Row sum (fixed-order tree -> deterministic) and the varying key bits of a row; all threads
+// return the same (sum in red_sum[0], diff).
+template <typename T>
+__device__ typename KeyTraits<T>::key_t block_sum_and_diff(const T *__restrict__ row, int64_t n,
+                                                           typename KeyTraits<T>::sum_t *red_sum,
+                                                           typename KeyTraits<T>::key_t *red_xor,
+                                                           typename KeyTraits<T>::key_t first_key)
+{
+    typedef KeyTraits<T> KT;
+    const int tid = threadIdx.x;
+    typename KT::sum_t acc = 0;
+    typename KT::key_t diff = 0;
     for (int64_t i = tid; i < n; i += SEL_THREADS) {
         const T v = row[i];
         acc += KT::to_sum(v);
@@ -711,89 +799,195 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
         if (tid < off) { red_sum[tid] += red_sum[tid + off]; red_xor[tid] |= red_xor[tid + off]; }
         __syncthreads();
     }
+    return red_xor[0];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
+    const T *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks,
+    int nranks, T *__restrict__ out /*[rows][nranks]*/,
+    typename KeyTraits<T>::sum_t *__restrict__ sums /*[rows]*/)
+{
+    typedef KeyTraits<T> KT;
+    typedef typename KT::key_t key_t;
+    typedef typename KT::sum_t sum_t;
+    __shared__ SelScratch<T> S;
+    __shared__ sum_t red_sum[SEL_THREADS];
+    __shared__ key_t red_xor[SEL_THREADS];
+    const T *row = data + (int64_t)blockIdx.x * ld;
+    const int tid = threadIdx.x;
+    const key_t first_key = KT::to_key(row[0]);
+    const key_t diff = block_sum_and_diff<T>(row, n, red_sum, red_xor, first_key);
     if (tid == 0 && sums) sums[blockIdx.x] = red_sum[0];
-    diff = red_xor[0];
-    // keys agree above bit `top`: those bits go straight into the prefix
-    int top = 0;
-    if (diff) top = (KT::BITS == 64) ? 64 - __clzll((long long)diff) : 32 - __clz((int)(uint32_t)diff);
-    const int npass = (top + 7) / 8;
+    if (tid < nranks) S.rem[tid] = ranks[tid];
+    __syncthreads();
+    block_radix_select<T>(row, n, nranks, S, first_key, diff);
+    if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(S.prefix[tid]);
+}
+
+// ------------------------------------------- sample-bracket select (int32 rows, n <= ~1e5)
+// The radix select above pays one shared-memory atomic per element in its first pass
+// (2 cycles per lane on the ATOMS path: 0.15 ms for the 16384 x 1290 pilot matrix).  The columns
+// of a row are i.i.d. samples, so: (1) sort a 1024-element sub-sample in shared memory, (2)
+// bracket every wanted rank between two of its order statistics (+-5 sigma of the rank),
+// (3) ONE pass over the row counting, with ballots only, the values below / equal to the ends
+// of each bracket, and collecting the few values strictly inside into a shared pool, (4) exact
+// radix select inside the pool.  If a rank falls outside its bracket or the pool overflows
+// (probability ~1e-6 per bracket, or heavy ties inside a bracket) the row is redone with the
+// radix select on the whole row: the result is exact either way.
+constexpr int SB_SAMPLE = 1024;
+constexpr int SB_POOL = 11264;             // ints; sample + pool = 48 KB of dynamic shared memory
+
+__global__ void __launch_bounds__(SEL_THREADS) vx_select_sb_kernel(
+    const int32_t *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks,
+    int nranks, int32_t *__restrict__ out, long long *__restrict__ sums,
+    unsigned int *__restrict__ fallbacks)
+{
+    typedef KeyTraits<int32_t> KT;
+    extern __shared__ int sb_dyn[];
+    int *smp = sb_dyn, *pool = sb_dyn + SB_SAMPLE;
+    __shared__ SelScratch<int32_t> S;
+    __shared__ long long red_sum[SEL_THREADS];
+    __shared__ uint32_t red_xor[SEL_THREADS];
+    __shared__ int brL[SEL_MAXR], brH[SEL_MAXR], ivL[SEL_MAXR], ivH[SEL_MAXR], rk2iv[SEL_MAXR];
+    __shared__ unsigned int cBelow[SEL_MAXR], cEqL[SEL_MAXR], cIn[SEL_MAXR], cEqH[SEL_MAXR];
+    __shared__ int nIv, poolFill, failed, valOut[SEL_MAXR], needPool[SEL_MAXR];
+    const int32_t *row = data + (int64_t)blockIdx.x * ld;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    // ---- pass 0: sum / varying bits, and the sub-sample (every (n/M)-th column)
+    const uint32_t first_key = KT::to_key(row[0]);
+    const uint32_t diff = block_sum_and_diff<int32_t>(row, n, red_sum, red_xor, first_key);
+    if (tid == 0 && sums) sums[blockIdx.x] = red_sum[0];
+    const int m = (int)min((int64_t)SB_SAMPLE, n);
+    for (int i = tid; i < SB_SAMPLE; i += SEL_THREADS)
+        smp[i] = (i < m) ? row[(int64_t)i * n / m] : 0x7fffffff;
+    if (tid < SEL_MAXR) { cBelow[tid] = cEqL[tid] = cIn[tid] = cEqH[tid] = 0; }
+    if (tid == 0) { poolFill = 0; failed = 0; }
+    __syncthreads();
+    // bitonic sort of the sample (ascending)
+    for (int k = 2; k <= SB_SAMPLE; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < SB_SAMPLE; i += SEL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const int a = smp[i], b = smp[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { smp[i] = b; smp[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // ---- brackets: rank r sits near sample position (r+0.5) m/n, +-5 sigma (+2)
     if (tid < nranks) {
-        rem[tid] = ranks[tid];
-        prefix[tid] = (npass * 8 >= KT::BITS) ? (key_t)0 : (first_key >> (npass * 8));
+        const double q = ((double)ranks[tid] + 0.5) / (double)n;
+        const double pos = q * m, sg = 5.0 * sqrt(fmax(m * q * (1.0 - q), 0.0)) + 2.0;
+        const int lo = (int)floor(pos - sg), hi = (int)ceil(pos + sg);
+        brL[tid] = lo < 0 ? (int)0x80000000 : smp[lo];
+        brH[tid] = hi >= m ? 0x7fffffff : smp[hi];
     }
     __syncthreads();
-
-    for (int pass = npass - 1; pass >= 0; --pass) {
-        const int shift = pass * 8;
-        if (tid == 0) {
-            int nd = 0;
-            for (int k = 0; k < nranks; ++k) {
-                int f = -1;
-                for (int d = 0; d < nd; ++d) if (dprefix[d] == prefix[k]) { f = d; break; }
-                if (f < 0) { f = nd; dprefix[nd++] = prefix[k]; }
-                hid[k] = f;
-            }
-            ndist = nd;
+    if (tid == 0) {   // ranks ascend, so do the brackets: merge overlapping ones into intervals
+        int g = -1;
+        for (int k = 0; k < nranks; ++k) {
+            if (g >= 0 && brL[k] <= ivH[g]) { ivH[g] = max(ivH[g], brH[k]); }
+            else { ++g; ivL[g] = brL[k]; ivH[g] = brH[k]; }
+            rk2iv[k] = g;
         }
-        for (int i = tid; i < SEL_MAXR * 256; i += SEL_THREADS) (&hist[0][0])[i] = 0;
-        __syncthreads();
-        const int nd = ndist;
-        const bool whole = (shift + 8 >= KT::BITS);
-        for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
-            const int64_t i = i0 + tid;
-            const bool in = i < n;
-            key_t key = 0, hi = 0;
-            uint32_t bin = 0;
-            if (in) {
-                key = KT::to_key(row[i]);
-                hi = whole ? (key_t)0 : (key >> (shift + 8));
-                bin = (uint32_t)(key >> shift) & 255u;
-            }
-            for (int d = 0; d < nd; ++d) {
-                const bool hit = in && (hi == dprefix[d]);
-                // warp-aggregate the common all-lanes-same-bin case (flat rows)
-                const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (m == 0) continue;
-                const int leader = __ffs(m) - 1;
-                const uint32_t lbin = __shfl_sync(0xffffffffu, bin, leader);
-                const uint32_t same = __ballot_sync(0xffffffffu, hit && bin == lbin);
-                if (same == m) {
-                    if ((tid & 31) == leader) atomicAdd(&hist[d][lbin], (uint32_t)__popc(m));
-                } else if (hit) {
-                    atomicAdd(&hist[d][bin], 1u);
+        nIv = g + 1;
+    }
+    __syncthreads();
+    // ---- the pass: ballots only; lane g of every warp keeps the counters of interval g
+    const int G = nIv;
+    unsigned int below = 0, eql = 0, inn = 0, eqh = 0;
+    for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
+        const int64_t i = i0 + tid;
+        const bool in = i < n;
+        const int v = in ? row[i] : 0;
+        bool collect = false;
+        for (int g = 0; g < G; ++g) {
+            const int L = ivL[g], H = ivH[g];
+            const uint32_t mb = __ballot_sync(0xffffffffu, in && v < L);
+            const uint32_t ml = __ballot_sync(0xffffffffu, in && v == L);
+            const bool inside = in && v > L && v < H;
+            const uint32_t mi = __ballot_sync(0xffffffffu, inside);
+            const uint32_t mh = __ballot_sync(0xffffffffu, in && v == H && H > L);
+            if (lane == g) { below += __popc(mb); eql += __popc(ml); inn += __popc(mi); eqh += __popc(mh); }
+            collect = collect || inside;
+        }
+        const uint32_t mc = __ballot_sync(0xffffffffu, collect);
+        if (mc) {
+            int base = 0;
+            if (lane == __ffs(mc) - 1) base = atomicAdd(&poolFill, __popc(mc));
+            base = __shfl_sync(0xffffffffu, base, __ffs(mc) - 1);
+            const int pos = base + __popc(mc & ((1u << lane) - 1u));
+            if (collect && pos < SB_POOL) pool[pos] = v;
+        }
+    }
+    if (lane < G) {
+        atomicAdd(&cBelow[lane], below); atomicAdd(&cEqL[lane], eql);
+        atomicAdd(&cIn[lane], inn); atomicAdd(&cEqH[lane], eqh);
+    }
+    __syncthreads();
+    // ---- resolve every rank inside its interval
+    if (tid < nranks) {
+        const int g = rk2iv[tid];
+        long long r = ranks[tid];
+        needPool[tid] = 0;
+        int bad = poolFill > SB_POOL;
+        if (r < (long long)cBelow[g]) bad = 1;
+        r -= cBelow[g];
+        if (!bad) {
+            if (r < (long long)cEqL[g]) valOut[tid] = ivL[g];
+            else {
+                r -= cEqL[g];
+                if (r < (long long)cIn[g]) {
+                    long long before = 0;               // pooled values of earlier intervals sort first
+                    for (int h = 0; h < g; ++h) before += cIn[h];
+                    S.rem[tid] = r + before;
+                    needPool[tid] = 1;
+                } else {
+                    r -= cIn[g];
+                    if (r < (long long)cEqH[g]) valOut[tid] = ivH[g];
+                    else bad = 1;
                 }
             }
         }
+        if (bad) atomicExch(&failed, 1);
+    }
+    __syncthreads();
+    if (failed) {                                      // exact fallback on the whole row
+        if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1u);
+        if (tid < nranks) S.rem[tid] = ranks[tid];
         __syncthreads();
-        if ((tid >> 5) < nranks) {           // warp w locates rank w in its 256-bin histogram
-            const int w = tid >> 5, l = tid & 31;
-            const uint32_t *h = hist[hid[w]] + 8 * l;
-            uint32_t c[8], lsum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { c[i] = h[i]; lsum += c[i]; }
-            long long incl = lsum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const long long y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (l >= o) incl += y;
-            }
-            const long long excl = incl - lsum, r = rem[w];
-            const uint32_t m = __ballot_sync(0xffffffffu, r >= excl && r < incl);
-            const int src = m ? __ffs(m) - 1 : 31;
-            if (l == src) {
-                long long cum = excl;
-                int i = 0;
-                for (; i < 7; ++i) {
-                    if (r < cum + (long long)c[i]) break;
-                    cum += c[i];
-                }
-                rem[w] = r - cum;
-                prefix[w] = (prefix[w] << 8) | (key_t)(8 * l + i);
-            }
+        block_radix_select<int32_t>(row, n, nranks, S, first_key, diff);
+        if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(S.prefix[tid]);
+        return;
+    }
+    // ranks that live in the pool: compact them to the front of the scratch
+    __shared__ int pk[SEL_MAXR], npk;
+    if (tid == 0) {
+        int c = 0;
+        for (int k = 0; k < nranks; ++k) if (needPool[k]) { const long long r = S.rem[k]; pk[c] = k; S.rem[c] = r; ++c; }
+        npk = c;                                       // (S.rem[c] <- S.rem[k], c <= k: in-place safe)
+    }
+    __syncthreads();
+    if (npk > 0) {
+        const int np_ = poolFill;
+        uint32_t pd = 0;
+        const uint32_t pfirst = KT::to_key(pool[0]);
+        for (int i = tid; i < np_; i += SEL_THREADS) pd |= KT::to_key(pool[i]) ^ pfirst;
+        red_xor[tid] = pd;
+        __syncthreads();
+        for (int off = SEL_THREADS / 2; off > 0; off >>= 1) {
+            if (tid < off) red_xor[tid] |= red_xor[tid + off];
+            __syncthreads();
         }
+        block_radix_select<int32_t>(pool, np_, npk, S, pfirst, red_xor[0]);
+        if (tid < npk) valOut[pk[tid]] = KT::from_key(S.prefix[tid]);
         __syncthreads();
     }
-    if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(prefix[tid]);
+    if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = valOut[tid];
 }
 
 // --------------------------------------------- order statistics out of merged windows
