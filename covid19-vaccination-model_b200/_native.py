@@ -22,7 +22,7 @@ SERIES = (
 VX_OK, VX_REFINE = 0, 1
 VX_ERR_NODEVICE = -5
 MODE_STOCHASTIC, MODE_EXPECTED = 0, 1
-DIRECT_MAX_DEFAULT = 131072   # vx_config.direct_max == 0 (csrc/vaxmc.cu: job_begin_common)
+DIRECT_MAX_DEFAULT = 65536   # vx_config.direct_max == 0 (csrc/vaxmc.cu: job_begin_common)
 
 
 class VaxmcError(RuntimeError):
@@ -107,7 +107,6 @@ SYMBOLS = {
     "vx_test_normal": (C.c_int, [_vp, C.c_int64, C.c_uint64, C.POINTER(C.c_float)]),
     "vx_test_select": (C.c_int, [_vp, _i32p, C.c_int64, C.c_int64, _i64p, C.c_int32, _i32p, _i64p]),
     "vx_launch_count": (C.c_int64, [_vp]),
-    "vx_select_fallbacks": (C.c_int64, [_vp]),
 }
 
 _LIB = None
@@ -219,10 +218,6 @@ class Context:
 
     def trim(self):
         self._ck(self._lib.vx_trim(self._h))
-
-    @property
-    def select_fallbacks(self) -> int:
-        return int(self._lib.vx_select_fallbacks(self._h))
 
     @property
     def launch_count(self) -> int:

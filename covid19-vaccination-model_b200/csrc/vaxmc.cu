@@ -36,9 +36,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int64_t SB_MAX_N = 98304;       // above this the brackets of a 1024-sample no longer fit the pool
-constexpr size_t SB_DYN_SMEM = sizeof(int) * (SB_SAMPLE + SB_POOL);
-
 // fixed-point scale of the p_soft_no moments when they travel in the int64 slab: sums of up
 // to 8e9 samples of values in [0,1] stay below 2^63, the mean keeps 9 digits
 constexpr double STATS_FIX = 1073741824.0;   // 2^30
@@ -98,7 +95,7 @@ struct Job {
 } // namespace
 
 enum Slot { SLOT_DUMP = 0, SLOT_ACC, SLOT_WINS, SLOT_TGT, SLOT_RES, SLOT_SEL_RANKS, SLOT_SEL_OUT,
-            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_PERM, SLOT_SORT, SLOT_SEL_FB, SLOT_COUNT };
+            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_PERM, SLOT_SORT, SLOT_COUNT };
 
 struct vx_ctx {
     // grow-only device workspace reused across jobs (cudaMalloc/cudaFree of the pilot matrix
@@ -120,8 +117,6 @@ struct vx_ctx {
     int64_t use_pilot = 1;
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
-    int64_t sb_select = 1;                // sample-bracket select for rows of <= SB_MAX_N values
-    int64_t sb_fallbacks = 0;             // rows the sample-bracket select redid with the radix select
     int sm_count = 148;
 };
 
@@ -440,28 +435,13 @@ int run_select_i32(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld,
       rc_ = pool_get(ctx, SLOT_SEL_OUT, sizeof(int32_t) * rows * K, &p_); if (rc_) return rc_; d_out = (int32_t *)p_;
       rc_ = pool_get(ctx, SLOT_SEL_SUMS, sizeof(long long) * rows, &p_); if (rc_) return rc_; d_sums = (long long *)p_; }
     CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, ctx->stream));
-    bool sorted = true;
-    for (int k = 1; k < K; ++k) sorted = sorted && ranks[k] >= ranks[k - 1];
-    unsigned int *d_fb = nullptr;
-    const bool use_sb = ctx->sb_select && sorted && n <= SB_MAX_N;
-    if (use_sb) {
-        void *p_ = nullptr;
-        int rc_ = pool_get(ctx, SLOT_SEL_FB, sizeof(unsigned int), &p_); if (rc_) return rc_;
-        d_fb = (unsigned int *)p_;
-        CK(cudaMemsetAsync(d_fb, 0, sizeof(unsigned int), ctx->stream));
-        vx_select_sb_kernel<<<(unsigned)rows, SEL_THREADS, SB_DYN_SMEM, ctx->stream>>>(d_data, ld, n, d_ranks, K, d_out, d_sums, d_fb);
-    } else {
-        vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
-    }
+    vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
     CKL();
     std::vector<int32_t> ho(rows * K);
     sums.resize(rows);
     CK(cudaMemcpyAsync(ho.data(), d_out, sizeof(int32_t) * rows * K, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(sums.data(), d_sums, sizeof(long long) * rows, cudaMemcpyDeviceToHost, ctx->stream));
-    unsigned int fb = 0;
-    if (d_fb) CK(cudaMemcpyAsync(&fb, d_fb, sizeof fb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->sb_fallbacks += fb;
     ord.resize(rows * K);
     for (int64_t i = 0; i < rows * K; ++i) ord[i] = ho[i];
     return VX_OK;
@@ -602,7 +582,6 @@ int vx_create(vx_ctx **out, int device)
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
         if (sm > 0) c->sm_count = sm;
         ctx = c;
-        cudaFuncSetAttribute(vx_select_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SB_DYN_SMEM);
         if (upload_rcp(ctx) != VX_OK) { g_create_error = c->err; cudaStreamDestroy(c->stream); delete c; return VX_ERR_CUDA; }
         *out = c;
         return VX_OK;
@@ -625,7 +604,6 @@ void vx_destroy(vx_ctx *ctx)
 const char *vx_last_error(vx_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int64_t vx_launch_count(vx_ctx *ctx) { return ctx ? ctx->launches : 0; }
-int64_t vx_select_fallbacks(vx_ctx *ctx) { return ctx ? ctx->sb_fallbacks : 0; }
 
 int vx_trim(vx_ctx *ctx)
 {
@@ -645,7 +623,6 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "use_pilot") ctx->use_pilot = value != 0;
     else if (s == "sort_samples") ctx->sort_samples = value != 0;
     else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
-    else if (s == "sb_select") ctx->sb_select = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }
@@ -704,7 +681,7 @@ static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_fir
     j->W = (cfg->T + 6) / 7;
     j->R = 2 * (int64_t)j->T + 2 * (int64_t)j->W;
     j->explicit_params = h_params != nullptr;
-    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 131072;
+    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 65536;   // crossover of direct vs pilot+fold on B200 (USA shape)
     j->direct = (cfg->mode == VX_MODE_EXPECTED) || cfg->n_samples <= dmax;
     j->t_begin = std::chrono::steady_clock::now();
     double nvmax_hi = std::max(cfg->bounds[10], cfg->bounds[11]);

@@ -825,171 +825,6 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
     if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(S.prefix[tid]);
 }
 
-// ------------------------------------------- sample-bracket select (int32 rows, n <= ~1e5)
-// The radix select above pays one shared-memory atomic per element in its first pass
-// (2 cycles per lane on the ATOMS path: 0.15 ms for the 16384 x 1290 pilot matrix).  The columns
-// of a row are i.i.d. samples, so: (1) sort a 1024-element sub-sample in shared memory, (2)
-// bracket every wanted rank between two of its order statistics (+-5 sigma of the rank),
-// (3) ONE pass over the row counting, with ballots only, the values below / equal to the ends
-// of each bracket, and collecting the few values strictly inside into a shared pool, (4) exact
-// radix select inside the pool.  If a rank falls outside its bracket or the pool overflows
-// (probability ~1e-6 per bracket, or heavy ties inside a bracket) the row is redone with the
-// radix select on the whole row: the result is exact either way.
-constexpr int SB_SAMPLE = 1024;
-constexpr int SB_POOL = 11264;             // ints; sample + pool = 48 KB of dynamic shared memory
-
-__global__ void __launch_bounds__(SEL_THREADS) vx_select_sb_kernel(
-    const int32_t *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks,
-    int nranks, int32_t *__restrict__ out, long long *__restrict__ sums,
-    unsigned int *__restrict__ fallbacks)
-{
-    typedef KeyTraits<int32_t> KT;
-    extern __shared__ int sb_dyn[];
-    int *smp = sb_dyn, *pool = sb_dyn + SB_SAMPLE;
-    __shared__ SelScratch<int32_t> S;
-    __shared__ long long red_sum[SEL_THREADS];
-    __shared__ uint32_t red_xor[SEL_THREADS];
-    __shared__ int brL[SEL_MAXR], brH[SEL_MAXR], ivL[SEL_MAXR], ivH[SEL_MAXR], rk2iv[SEL_MAXR];
-    __shared__ unsigned int cBelow[SEL_MAXR], cEqL[SEL_MAXR], cIn[SEL_MAXR], cEqH[SEL_MAXR];
-    __shared__ int nIv, poolFill, failed, valOut[SEL_MAXR], needPool[SEL_MAXR];
-    const int32_t *row = data + (int64_t)blockIdx.x * ld;
-    const int tid = threadIdx.x, lane = tid & 31;
-
-    // ---- pass 0: sum / varying bits, and the sub-sample (every (n/M)-th column)
-    const uint32_t first_key = KT::to_key(row[0]);
-    const uint32_t diff = block_sum_and_diff<int32_t>(row, n, red_sum, red_xor, first_key);
-    if (tid == 0 && sums) sums[blockIdx.x] = red_sum[0];
-    const int m = (int)min((int64_t)SB_SAMPLE, n);
-    for (int i = tid; i < SB_SAMPLE; i += SEL_THREADS)
-        smp[i] = (i < m) ? row[(int64_t)i * n / m] : 0x7fffffff;
-    if (tid < SEL_MAXR) { cBelow[tid] = cEqL[tid] = cIn[tid] = cEqH[tid] = 0; }
-    if (tid == 0) { poolFill = 0; failed = 0; }
-    __syncthreads();
-    // bitonic sort of the sample (ascending)
-    for (int k = 2; k <= SB_SAMPLE; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < SB_SAMPLE; i += SEL_THREADS) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const int a = smp[i], b = smp[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { smp[i] = b; smp[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    // ---- brackets: rank r sits near sample position (r+0.5) m/n, +-5 sigma (+2)
-    if (tid < nranks) {
-        const double q = ((double)ranks[tid] + 0.5) / (double)n;
-        const double pos = q * m, sg = 5.0 * sqrt(fmax(m * q * (1.0 - q), 0.0)) + 2.0;
-        const int lo = (int)floor(pos - sg), hi = (int)ceil(pos + sg);
-        brL[tid] = lo < 0 ? (int)0x80000000 : smp[lo];
-        brH[tid] = hi >= m ? 0x7fffffff : smp[hi];
-    }
-    __syncthreads();
-    if (tid == 0) {   // ranks ascend, so do the brackets: merge overlapping ones into intervals
-        int g = -1;
-        for (int k = 0; k < nranks; ++k) {
-            if (g >= 0 && brL[k] <= ivH[g]) { ivH[g] = max(ivH[g], brH[k]); }
-            else { ++g; ivL[g] = brL[k]; ivH[g] = brH[k]; }
-            rk2iv[k] = g;
-        }
-        nIv = g + 1;
-    }
-    __syncthreads();
-    // ---- the pass: ballots only; lane g of every warp keeps the counters of interval g
-    const int G = nIv;
-    unsigned int below = 0, eql = 0, inn = 0, eqh = 0;
-    for (int64_t i0 = 0; i0 < n; i0 += SEL_THREADS) {
-        const int64_t i = i0 + tid;
-        const bool in = i < n;
-        const int v = in ? row[i] : 0;
-        bool collect = false;
-        for (int g = 0; g < G; ++g) {
-            const int L = ivL[g], H = ivH[g];
-            const uint32_t mb = __ballot_sync(0xffffffffu, in && v < L);
-            const uint32_t ml = __ballot_sync(0xffffffffu, in && v == L);
-            const bool inside = in && v > L && v < H;
-            const uint32_t mi = __ballot_sync(0xffffffffu, inside);
-            const uint32_t mh = __ballot_sync(0xffffffffu, in && v == H && H > L);
-            if (lane == g) { below += __popc(mb); eql += __popc(ml); inn += __popc(mi); eqh += __popc(mh); }
-            collect = collect || inside;
-        }
-        const uint32_t mc = __ballot_sync(0xffffffffu, collect);
-        if (mc) {
-            int base = 0;
-            if (lane == __ffs(mc) - 1) base = atomicAdd(&poolFill, __popc(mc));
-            base = __shfl_sync(0xffffffffu, base, __ffs(mc) - 1);
-            const int pos = base + __popc(mc & ((1u << lane) - 1u));
-            if (collect && pos < SB_POOL) pool[pos] = v;
-        }
-    }
-    if (lane < G) {
-        atomicAdd(&cBelow[lane], below); atomicAdd(&cEqL[lane], eql);
-        atomicAdd(&cIn[lane], inn); atomicAdd(&cEqH[lane], eqh);
-    }
-    __syncthreads();
-    // ---- resolve every rank inside its interval
-    if (tid < nranks) {
-        const int g = rk2iv[tid];
-        long long r = ranks[tid];
-        needPool[tid] = 0;
-        int bad = poolFill > SB_POOL;
-        if (r < (long long)cBelow[g]) bad = 1;
-        r -= cBelow[g];
-        if (!bad) {
-            if (r < (long long)cEqL[g]) valOut[tid] = ivL[g];
-            else {
-                r -= cEqL[g];
-                if (r < (long long)cIn[g]) {
-                    long long before = 0;               // pooled values of earlier intervals sort first
-                    for (int h = 0; h < g; ++h) before += cIn[h];
-                    S.rem[tid] = r + before;
-                    needPool[tid] = 1;
-                } else {
-                    r -= cIn[g];
-                    if (r < (long long)cEqH[g]) valOut[tid] = ivH[g];
-                    else bad = 1;
-                }
-            }
-        }
-        if (bad) atomicExch(&failed, 1);
-    }
-    __syncthreads();
-    if (failed) {                                      // exact fallback on the whole row
-        if (tid == 0 && fallbacks) atomicAdd(fallbacks, 1u);
-        if (tid < nranks) S.rem[tid] = ranks[tid];
-        __syncthreads();
-        block_radix_select<int32_t>(row, n, nranks, S, first_key, diff);
-        if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(S.prefix[tid]);
-        return;
-    }
-    // ranks that live in the pool: compact them to the front of the scratch
-    __shared__ int pk[SEL_MAXR], npk;
-    if (tid == 0) {
-        int c = 0;
-        for (int k = 0; k < nranks; ++k) if (needPool[k]) { const long long r = S.rem[k]; pk[c] = k; S.rem[c] = r; ++c; }
-        npk = c;                                       // (S.rem[c] <- S.rem[k], c <= k: in-place safe)
-    }
-    __syncthreads();
-    if (npk > 0) {
-        const int np_ = poolFill;
-        uint32_t pd = 0;
-        const uint32_t pfirst = KT::to_key(pool[0]);
-        for (int i = tid; i < np_; i += SEL_THREADS) pd |= KT::to_key(pool[i]) ^ pfirst;
-        red_xor[tid] = pd;
-        __syncthreads();
-        for (int off = SEL_THREADS / 2; off > 0; off >>= 1) {
-            if (tid < off) red_xor[tid] |= red_xor[tid + off];
-            __syncthreads();
-        }
-        block_radix_select<int32_t>(pool, np_, npk, S, pfirst, red_xor[0]);
-        if (tid < npk) valOut[pk[tid]] = KT::from_key(S.prefix[tid]);
-        __syncthreads();
-    }
-    if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = valOut[tid];
-}
-
 // --------------------------------------------- order statistics out of merged windows
 // np.quantile(method="linear"): virtual index (n-1)*q -> the two neighbouring ranks
 // (numpy/lib/_function_base_impl.py: _get_indexes).  Same arithmetic on host and device.

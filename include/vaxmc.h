@@ -106,8 +106,7 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * "pilot_sigmas" (half-width of the pilot bracket in rank sigmas, default 6),
  * "use_pilot" (0: start from the coarse full-range windows), "sort_samples" (0: fold the
  * shard in id order instead of pressure-bucket order; same integers either way), "chunk_samples"
- * (granularity of the max_running_time check, default 2^20), "sb_select" (0: always use
- * the plain radix select for the pilot/direct order statistics).                        */
+ * (granularity of the max_running_time check, default 2^20).                          */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
  * vx_trim returns it to the driver. */
@@ -182,8 +181,6 @@ int vx_test_select(vx_ctx *ctx, const int32_t *data, int64_t rows, int64_t n,
                    int64_t *sums /*[rows]*/);
 /* number of kernels this context has launched since creation (bench.py gpu_launches)   */
 int64_t vx_launch_count(vx_ctx *ctx);
-/* rows that the sample-bracket select had to redo with the full radix select (diagnostic) */
-int64_t vx_select_fallbacks(vx_ctx *ctx);
 
 #ifdef __cplusplus
 }

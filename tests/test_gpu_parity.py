@@ -110,41 +110,29 @@ def test_normal_pair_law(ctx):
     assert np.abs(z).max() < 7.0
 
 
-@pytest.mark.parametrize("sb", [1, 0])
-def test_select_kernels_exact(ctx, sb):
-    """Order statistics + sums of the pilot/direct matrix: sample-bracket select (sb=1, with its
-    radix fallback) and the plain radix select (sb=0) against np.sort."""
+def test_radix_select_exact(ctx):
+    """Order statistics + sums of the pilot/direct matrix against np.sort."""
     rng = np.random.default_rng(1)
-    ctx.set_option("sb_select", sb)
-    try:
-        for n in (70001, 16384, 98304, 200000):
-            data = np.stack([
-                rng.integers(0, 350000, n), rng.integers(0, 5, n), np.zeros(n, dtype=np.int64),
-                np.full(n, 2**27 - 1), rng.poisson(3000, n), np.arange(n)[::-1],
-                (rng.random(n) < 0.3) * rng.integers(0, 1 << 26, n), rng.integers(0, 2, n) * 50000,
-                np.where(rng.random(n) < 0.97, 0, rng.integers(1, 1000, n)),       # 97 % ties at 0
-                np.sort(rng.integers(0, 1 << 20, n)),                              # NOT i.i.d. columns
-                rng.poisson(0.02, n), rng.integers(0, 1 << 27, n),
-            ]).astype(np.int32)
-            ranks = sorted([0, 1, n // 40, n // 40 + 1, n // 2, n - n // 40, n - 2, n - 1])
-            before = ctx.select_fallbacks
-            got, sums = ctx.test_select(data, ranks)
-            want = np.sort(data, axis=1)[:, ranks]
-            assert np.array_equal(got, want), n
-            assert np.array_equal(sums, data.astype(np.int64).sum(axis=1))
-            if not sb or n > 98304:
-                assert ctx.select_fallbacks == before
-        # unsorted rank lists and tiny rows
-        d = rng.integers(0, 1000, (3, 5000)).astype(np.int32)
-        got, _ = ctx.test_select(d, [4999, 0, 2500])
-        assert np.array_equal(got, np.sort(d, axis=1)[:, [4999, 0, 2500]])
-        for m in (1, 2, 31, 33, 513, 1024, 1025):
-            d = rng.integers(0, 1000, (3, m)).astype(np.int32)
-            rk = sorted({0, m // 2, m - 1})
-            got, sums = ctx.test_select(d, rk)
-            assert np.array_equal(got, np.sort(d, axis=1)[:, rk]), m
-    finally:
-        ctx.set_option("sb_select", 1)
+    for n in (70001, 16384, 200000):
+        data = np.stack([
+            rng.integers(0, 350000, n), rng.integers(0, 5, n), np.zeros(n, dtype=np.int64),
+            np.full(n, 2**27 - 1), rng.poisson(3000, n), np.arange(n)[::-1],
+            (rng.random(n) < 0.3) * rng.integers(0, 1 << 26, n), rng.integers(0, 2, n) * 50000,
+            np.where(rng.random(n) < 0.97, 0, rng.integers(1, 1000, n)),       # 97 % ties at 0
+            np.sort(rng.integers(0, 1 << 20, n)), rng.poisson(0.02, n), rng.integers(0, 1 << 27, n),
+        ]).astype(np.int32)
+        ranks = sorted([0, 1, n // 40, n // 40 + 1, n // 2, n - n // 40, n - 2, n - 1])
+        got, sums = ctx.test_select(data, ranks)
+        assert np.array_equal(got, np.sort(data, axis=1)[:, ranks]), n
+        assert np.array_equal(sums, data.astype(np.int64).sum(axis=1))
+    d = rng.integers(0, 1000, (3, 5000)).astype(np.int32)
+    got, _ = ctx.test_select(d, [4999, 0, 2500])                                # unsorted rank list
+    assert np.array_equal(got, np.sort(d, axis=1)[:, [4999, 0, 2500]])
+    for m in (1, 2, 31, 33, 513, 1024, 1025):                                    # tiny rows
+        d = rng.integers(0, 1000, (3, m)).astype(np.int32)
+        rk = sorted({0, m // 2, m - 1})
+        got, sums = ctx.test_select(d, rk)
+        assert np.array_equal(got, np.sort(d, axis=1)[:, rk]), m
 
 
 # ------------------------------------------------------ (1) expected-value parity
@@ -365,7 +353,7 @@ def test_streamed_equals_direct(vax, ctx, q):
     dict(T=100, n=40001, N=1000, bounds="usa"),                    # ragged warp, tiny population
     dict(T=371, n=20000, N=1000000, bounds="wide"),                # lam up to ~1e5, deliveries ~1e6
     dict(T=200, n=30000, N=50000, bounds="reject"),                # rejection-heavy parameter draw
-    dict(T=564, n=131073, N=50000, bounds="usa", q=(0.1, 0.9)),    # just above the default direct_max
+    dict(T=564, n=65537, N=50000, bounds="usa", q=(0.1, 0.9)),     # just above the default direct_max
 ])
 def test_streamed_equals_direct_edge_shapes(vax, ctx, case):
     b = {"usa": usa_bounds_frac(), "wide": wide_bounds_frac(),
