@@ -15,12 +15,12 @@ model (the reference's run_model / CLI interface), distributed (sample sharding 
 from . import _native, build, distributed, model  # noqa: F401
 from ._native import Context, VaxmcError, default_context  # noqa: F401
 from .model import (  # noqa: F401
-    SERIES, cache_clear, main, results_to_jsonable, run_model, run_model_grid, run_sampling,
+    SERIES, cache_clear, main, results_to_jsonable, run_model, run_model_grid, run_model_quantiles, run_sampling,
     run_single_realization, sample_param_combinations, seed,
 )
 
 __all__ = [
-    "run_model", "run_model_grid", "run_sampling", "sample_param_combinations", "run_single_realization", "seed",
+    "run_model", "run_model_grid", "run_model_quantiles", "run_sampling", "sample_param_combinations", "run_single_realization", "seed",
     "main", "SERIES", "Context", "VaxmcError", "default_context", "cache_clear",
     "results_to_jsonable",
 ]

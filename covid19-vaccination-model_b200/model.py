@@ -255,6 +255,47 @@ def run_model_grid(boxes, CI, n_rep, N, date_range, *, seeds=None, device=None, 
     return res
 
 
+def run_model_quantiles(p_pro_bounds, p_anti_bounds, pressure_bounds, tau_bounds, nv_0_bounds,
+                        nv_max_bounds, quantiles, n_rep, N, date_range, *, seed=None, device=None,
+                        direct_max=0, pilot_samples=0):
+    """Fan chart: arbitrary quantile FRACTIONS of the same Monte Carlo sample.
+
+    The engine extracts two exact quantiles per job; because a sample's trajectory depends only
+    on (seed, sample id), jobs that share the seed see the very same trajectories, so the
+    fractions are served pairwise by ceil(len/2) jobs and are mutually consistent (monotone in q,
+    equal to np.quantile over one common sample).  Returns (model_results, msg_error,
+    msg_agnostics_pct) where each series carries "mean", "dates" and "quantiles": {q: array}.
+    """
+    qs = sorted(float(q) for q in quantiles)
+    if not qs or qs[0] < 0.0 or qs[-1] > 1.0:
+        raise ValueError("quantiles must be fractions in [0, 1]")
+    key_seed, _ = _next_seed(seed)
+    bounds = _bounds12(np.array(p_pro_bounds) / 100, np.array(p_anti_bounds) / 100,
+                       np.array(pressure_bounds), np.array(tau_bounds), np.array(nv_0_bounds) / 100,
+                       np.array(nv_max_bounds) / 100)
+    daily, weekly = _dates(date_range["start_date"], date_range["end_date"])
+    from . import distributed as dist_
+
+    pairs = [(qs[i], qs[-1 - i]) for i in range((len(qs) + 1) // 2)]     # outermost pair first
+    results = None
+    msg = "Agnosticts: "
+    for q_lo, q_hi in pairs:
+        cfg = nat.make_config(bounds, N, len(daily), n_rep, key_seed, q_lo, q_hi, direct_max=direct_max,
+                              pilot_samples=pilot_samples)
+        out = dist_.run_job(cfg, device=device)
+        if out.c.aborted:
+            return None, MSG_ERR_BOUNDS, "Agnosticts: "
+        if results is None:
+            msg = _agnostics_message(out.c.soft_no_mean, out.c.soft_no_std)
+            results = {k: {"mean": out.mean[s], "dates": weekly if s == 1 else daily, "quantiles": {}}
+                       for s, k in enumerate(SERIES)}
+            results["number_finished_samples"] = int(out.c.n_finished)
+        for s, k in enumerate(SERIES):
+            results[k]["quantiles"][q_lo] = out.lower[s]
+            results[k]["quantiles"][q_hi] = out.upper[s]
+    return results, "", msg
+
+
 def run_sampling(params, start_date, end_date, CI, N, max_running_time=None, *, seed=None,
                  device=None, mode="stochastic", direct_max=0, pilot_samples=0):
     """model.py:139-228 over EXPLICIT parameter tuples (CI is the fraction, as there)."""

@@ -590,3 +590,23 @@ def test_integration_md_stub_runs_and_matches(vax):
         for f in ("mean", "lower", "upper"):
             assert np.array_equal(data[k][f], ours[k][f]), (k, f)
         assert list(data[k]["dates"]) == list(ours[k]["dates"])
+
+
+def test_run_model_quantiles_fan_is_exact(vax, ctx):
+    """N3: any set of quantile fractions of ONE sample (jobs sharing the seed see the same
+    trajectories): equal to np.quantile over the dumped integers, streamed and direct."""
+    qs = [0.05, 0.25, 0.5, 0.75, 0.95, 0.99, 0.01]
+    n, N, T, W = 30000, 50000, USA_T, USA_W
+    counts = ctx.dump_counts(_cfg(vax, usa_bounds_frac(), n, seed=77), 0, n).astype(np.int64)
+    vals = [(counts[:T] / N) * 100, counts[T:T + W] * 1e6 / N,
+            np.repeat(counts[T + W:T + 2 * W], 7, axis=0)[:T] * 100 / N, counts[T + 2 * W:] * 100 / N]
+    for dm in (1 << 20, 1):
+        res, err, msg = vax.run_model_quantiles([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10],
+                                                qs, n, N, USA_DATES, seed=77, direct_max=dm, pilot_samples=4096)
+        assert err == "" and res["number_finished_samples"] == n
+        for s, k in enumerate(SERIES):
+            assert sorted(res[k]["quantiles"]) == sorted(qs)
+            want = np.quantile(vals[s], sorted(qs), axis=1)
+            for i, q in enumerate(sorted(qs)):
+                assert np.array_equal(res[k]["quantiles"][q], want[i]), (k, q, dm)
+            assert np.allclose(res[k]["mean"], vals[s].mean(axis=1), rtol=1e-13, atol=1e-13)
