@@ -117,6 +117,7 @@ struct vx_ctx {
     int64_t use_pilot = 1;
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
+    int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
     int sm_count = 148;
 };
 
@@ -461,7 +462,8 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
     a.dump = d_dump;
     a.dump_stride = ld;
     const int64_t grid = (count + SIM_THREADS - 1) / SIM_THREADS;
-    vx_sim_kernel<SIM_DUMP><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+    if (ctx->exact_poisson) vx_sim_kernel<SIM_DUMP, 1><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+    else vx_sim_kernel<SIM_DUMP, 0><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
     CKL();
     return VX_OK;
 }
@@ -623,6 +625,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "use_pilot") ctx->use_pilot = value != 0;
     else if (s == "sort_samples") ctx->sort_samples = value != 0;
     else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
+    else if (s == "exact_poisson") ctx->exact_poisson = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }
@@ -905,7 +908,8 @@ int vx_job_accumulate(vx_ctx *ctx)
             j->d_perm = nullptr;      // the pool slot now holds this chunk's order
         }
         const int64_t grid = (cnt + SIM_THREADS - 1) / SIM_THREADS;
-        vx_sim_kernel<SIM_FOLD><<<(unsigned)grid, SIM_THREADS, (size_t)ctx->fold_pad_smem, ctx->stream>>>(a);
+        if (ctx->exact_poisson) vx_sim_kernel<SIM_FOLD, 1><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+        else vx_sim_kernel<SIM_FOLD, 0><<<(unsigned)grid, SIM_THREADS, (size_t)ctx->fold_pad_smem, ctx->stream>>>(a);
         CKL();
         j->fold_launches++;
         done += cnt;
@@ -1186,7 +1190,7 @@ int vx_test_poisson(vx_ctx *ctx, double lam, int64_t n, uint64_t seed, int32_t *
     if (n < 1 || !out_host) return fail(ctx, VX_ERR_ARG, "bad argument");
     int32_t *d = nullptr;
     CK(cudaMalloc(&d, sizeof(int32_t) * n));
-    vx_test_poisson_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((float)lam, n, seed, d);
+    vx_test_poisson_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((float)lam, n, seed, d, (int)ctx->exact_poisson);
     CKL();
     CK(cudaMemcpyAsync(out_host, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -168,6 +168,46 @@ __device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
     return x;
 }
 
+// Exact Poisson(lam) variate -- validation mode ("exact_poisson" option), numpy's regime
+// structure on the Philox stream: lam < 10 inversion (exact up to fp32 rounding of the CDF),
+// lam >= 10 Hoermann's PTRS transformed rejection ("The transformed rejection method for
+// generating Poisson random variables", 1993 -- the algorithm numpy's legacy poisson uses).
+// The acceptance test is evaluated in fp64 (k*log(lam) - lgamma(k+1) cancels catastrophically
+// in fp32 at lam ~ 1e4).  Extra uniforms come from Philox blocks (tag TAG_PTRS, index =
+// 2*(8*day + attempt block) + draw); ~3x slower than poisson_draw, so not the default.
+enum : uint32_t { TAG_PTRS = 4 };
+
+__device__ __noinline__ int poisson_draw_exact(float lam, uint32_t w, uint32_t s_lo, uint32_t s_hi,
+                                               uint32_t day, uint32_t which, const PhiloxKeys &K)
+{
+    if (!(lam > 0.0f)) return 0;
+    if (lam < 10.0f) {
+        const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
+        float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
+        int x = 0;
+        while (u >= cdf && x < 70) { ++x; p *= lam * c_rcp[x]; cdf += p; }
+        return x;
+    }
+    const double L = (double)lam, slam = sqrt(L), loglam = log(L);
+    const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2);
+    for (uint32_t blk = 0;; ++blk) {
+        const uint4 r = philox4x32_10(s_lo, s_hi, 2u * (8u * day + (blk & 7u)) + which + 16384u * (blk >> 3),
+                                      TAG_PTRS, K);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double U = ((double)(h ? r.z : r.x) + 0.5) * 2.3283064365386963e-10 - 0.5;
+            const double V = ((double)(h ? r.w : r.y) + 0.5) * 2.3283064365386963e-10;
+            const double us = 0.5 - fabs(U);
+            const double kf = floor((2 * a / us + b) * U + L + 0.43);
+            if (us >= 0.07 && V <= vr) return (int)kf;
+            if (kf < 0 || (us < 0.013 && V > us)) continue;
+            if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -L + kf * loglam - lgamma(kf + 1))
+                return (int)kf;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ parameter draw
 struct SampleParams { double p_pro, p_anti, pressure, tau, nv0, nvmax; };
 
@@ -378,8 +418,8 @@ constexpr int SIM_THREADS = 128;       // warps are independent: small CTAs = sh
 
 enum { SIM_DUMP = 0, SIM_FOLD = 1 };
 
-template <int MODE>
-__global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(const SimArgs a)
+template <int MODE, int EXACT = 0>
+__global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_sim_kernel(const SimArgs a)
 {
     __shared__ __align__(16) int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -446,12 +486,14 @@ __global__ void __launch_bounds__(SIM_THREADS, VX_SIM_MINBLOCKS) vx_sim_kernel(c
                 normal_pair(r.x, r.y, z1, z2);
                 // ---- vaccination draw, model.py:102-112
                 const float lam1 = (float)n_wait * ((float)stock * c1);
-                int dv = poisson_draw(lam1, z1, r.z);
+                int dv = EXACT ? poisson_draw_exact(lam1, r.z, s_lo, s_hi, (uint32_t)day, 0u, a.keys)
+                               : poisson_draw(lam1, z1, r.z);
                 dv = min(dv, min(stock, n_wait));
                 n_vacc += dv; n_wait -= dv; stock -= dv;
                 // ---- conversion draw, model.py:115-120
                 const float lam2 = (float)n_agn * ((float)n_vacc * c2);
-                int da = poisson_draw(lam2, z2, r.w);
+                int da = EXACT ? poisson_draw_exact(lam2, r.w, s_lo, s_hi, (uint32_t)day, 1u, a.keys)
+                               : poisson_draw(lam2, z2, r.w);
                 da = min(da, n_agn);
                 n_agn -= da; n_wait += da;
                 // ---- recording, model.py:124-127 and the weekly series :196-214
@@ -904,7 +946,7 @@ __global__ void vx_test_philox_kernel(uint4 ctr, uint2 key, uint32_t *out)
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 
-__global__ void vx_test_poisson_kernel(float lam, int64_t n, uint64_t seed, int32_t *out)
+__global__ void vx_test_poisson_kernel(float lam, int64_t n, uint64_t seed, int32_t *out, int exact)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -912,6 +954,11 @@ __global__ void vx_test_poisson_kernel(float lam, int64_t n, uint64_t seed, int3
                                   (uint32_t)(seed >> 32));
     float z1, z2;
     normal_pair(r.x, r.y, z1, z2);
+    if (exact) {
+        const PhiloxKeys K = philox_keys(seed);
+        out[i] = poisson_draw_exact(lam, r.z, (uint32_t)i, (uint32_t)(i >> 32), 3u, 0u, K);
+        return;
+    }
     out[i] = poisson_draw(lam, (i & 1) ? z2 : z1, (i & 1) ? r.w : r.z);
 }
 

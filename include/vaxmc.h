@@ -106,7 +106,8 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * "pilot_sigmas" (half-width of the pilot bracket in rank sigmas, default 6),
  * "use_pilot" (0: start from the coarse full-range windows), "sort_samples" (0: fold the
  * shard in id order instead of pressure-bucket order; same integers either way), "chunk_samples"
- * (granularity of the max_running_time check, default 2^20).                          */
+ * (granularity of the max_running_time check, default 2^20), "exact_poisson" (1: validation
+ * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; ~3x slower). */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
  * vx_trim returns it to the driver. */

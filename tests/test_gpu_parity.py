@@ -610,3 +610,53 @@ def test_run_model_quantiles_fan_is_exact(vax, ctx):
             for i, q in enumerate(sorted(qs)):
                 assert np.array_equal(res[k]["quantiles"][q], want[i]), (k, q, dm)
             assert np.allclose(res[k]["mean"], vals[s].mean(axis=1), rtol=1e-13, atol=1e-13)
+
+
+def _chi2_p(x, lam, n):
+    lo = max(int(stats.poisson.ppf(1e-5, lam)), 0)
+    hi = int(stats.poisson.ppf(1 - 1e-5, lam)) + 1
+    edges = np.arange(lo, hi + 1)[::max(1, (hi + 1 - lo) // 200)]
+    cdf = stats.poisson.cdf(edges - 1, lam)
+    probs = np.diff(np.concatenate([[0.0], cdf[1:], [1.0]]))
+    obs = np.histogram(x, bins=np.concatenate([[-0.5], edges[1:] - 0.5, [np.inf]]))[0]
+    keep = probs * n >= 50
+    pk = np.concatenate([probs[keep], [probs[~keep].sum()]])
+    ok = np.concatenate([obs[keep], [obs[~keep].sum()]])
+    if pk[-1] * n < 5:
+        pk[-2] += pk[-1]; ok[-2] += ok[-1]; pk, ok = pk[:-1], ok[:-1]
+    return stats.chi2.sf(((ok - n * pk) ** 2 / (n * pk)).sum(), len(pk) - 1)
+
+
+def test_exact_poisson_mode(vax, ctx):
+    """The validation sampler (inversion < 10, PTRS >= 10 with an fp64 acceptance test): exact law
+    per lambda, and GPU-vs-GPU agreement of whole trajectories with the default sampler on one
+    tuple (pure sampler noise) at 1e6 samples per arm."""
+    n = 2_000_000
+    ctx.set_option("exact_poisson", 1)
+    try:
+        for lam in (0.5, 9.999, 10.0, 12.0, 63.0, 2857.0, 1e5):
+            x = ctx.test_poisson(lam, n, seed=77 + int(lam)).astype(np.int64)
+            assert abs(x.mean() - lam) < 5 * np.sqrt(lam / n) + 1e-6 * lam
+            assert _chi2_p(x, lam, n) > 1e-4, lam
+        m = 1_000_000
+        params = np.tile(np.array([0.4, 0.2, 0.01, 6.0, 0.011, 0.07]), (m, 1))
+        cfgx = vax._native.make_config(np.zeros(12), 50000, 200, m, 5, 0.025, 0.975, direct_max=1 << 21)
+        _, exact = ctx.run_params(cfgx, params, want_counts=True)
+    finally:
+        ctx.set_option("exact_poisson", 0)
+    _, fast = ctx.run_params(cfgx, params, want_counts=True)
+    assert not np.array_equal(exact, fast)                      # different samplers, different draws
+    T, W = 200, 29
+    assert np.array_equal(exact[T + W:T + 2 * W], fast[T + W:T + 2 * W])     # deliveries: deterministic
+    pv = []
+    for r in list(range(0, T, 7)) + list(range(T, T + W)) + list(range(T + 2 * W, 2 * T + 2 * W, 7)):
+        a, b = exact[r], fast[r]
+        if a.min() == a.max() and b.min() == b.max():
+            continue
+        pv.append(stats.ks_2samp(a, b, method="asymp").pvalue)
+        sd = max(a.std(), b.std())
+        assert abs(a.mean() - b.mean()) < 6 * sd * np.sqrt(2 / m) + 1e-9, r
+    pv = np.array(pv)
+    assert pv.min() > 0.01 / len(pv) and (pv < 0.01).mean() <= 0.04, (pv.min(), (pv < 0.01).mean())
+    print(f"\nexact vs default sampler, {m} samples per arm: {len(pv)} KS tests, min p={pv.min():.4f}, "
+          f"median p={np.median(pv):.3f}")
