@@ -118,8 +118,8 @@ __constant__ float c_rcp[72];
 
 // Poisson(lam) variate.
 //   lam == 0          -> 0 (numpy returns 0 without consuming the stream, model.py:104,116)
-//   0 < lam < 4       -> exact inversion by sequential search with one uniform (word w)
-//   lam >= 4          -> floor of the continuous inverse Q(z) of the Poisson CDF expanded
+//   0 < lam < 2       -> exact inversion by sequential search with one uniform (word w)
+//   lam >= 2          -> floor of the continuous inverse Q(z) of the Poisson CDF expanded
 //                        around the normal quantile z (Cornish-Fisher with the lattice
 //                        correction; the first three orders are Giles' Q_N1, ACM TOMS 42(1),
 //                        2016):
@@ -128,14 +128,17 @@ __constant__ float c_rcp[72];
 //                              + (a1 z + a3 z^3 + a5 z^5)/lam^1.5
 //                              + (b0 + b2 z^2 + b4 z^4 + b6 z^6)/lam^2,      s = sqrt(lam)
 //                        The two highest orders are a weighted least-squares fit of the exact
-//                        jump points Phi^-1(F(k)) -> k+1 over lam in [4,32] (their asymptotic
+//                        jump points Phi^-1(F(k)) -> k+1 over lam in [2,32] (their asymptotic
 //                        values are a=(.01725,-.00352,-.00133), b=(-.0015,-.0113,.0013,.0006));
 //                        oracle/fit_poisson_cf.py regenerates them and prints the resulting
-//                        sup-CDF error against the exact law: 6.6e-5 at lam=4, <=1.8e-5 for
-//                        lam>=5, <5e-6 for lam>=16 (tests/test_sampler_math.py pins these).
-constexpr float POISSON_INV_MAX = 4.0f;
-constexpr float CF_A1 = 0.01534796f, CF_A3 = 0.00120633f, CF_A5 = -0.00210642f;
-constexpr float CF_B0 = 0.00125185f, CF_B2 = -0.01826666f, CF_B4 = 0.00198713f, CF_B6 = 0.00056336f;
+//                        sup-CDF error against the exact law: <=1.5e-4 on [2,3], 6.4e-5 at 3.5,
+//                        <=4.8e-5 for lam>=4, <=1.5e-5 for lam>=10, <2e-6 for lam>=32
+//                        (tests/test_sampler_math.py pins these).  The threshold is where
+//                        the divergent inversion loop stops paying: at 10 (numpy's) it was
+//                        43 % of all issued instructions, at 4 it was 10 %, at 2 it is 4 %.
+constexpr float POISSON_INV_MAX = 2.0f;
+constexpr float CF_A1 = 0.01865529f, CF_A3 = 0.00004626f, CF_A5 = -0.00184102f;
+constexpr float CF_B0 = 0.00100592f, CF_B2 = -0.01903893f, CF_B4 = 0.00285482f, CF_B6 = 0.00029421f;
 
 __device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
 {

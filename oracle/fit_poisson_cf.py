@@ -1,6 +1,6 @@
 """oracle/fit_poisson_cf.py -- derivation of the Poisson sampler's normal-quantile expansion.
 
-TEST/DESIGN INFRASTRUCTURE (not product code).  The device sampler for lam >= 4
+TEST/DESIGN INFRASTRUCTURE (not product code).  The device sampler for lam >= 2
 (csrc/vaxmc_kernels.cuh: poisson_draw) returns floor(Q(z)), z ~ N(0,1), with
 
     Q = lam + s z + (1/3 + z^2/6) + (-z/36 - z^3/72)/s + (-8/405 + 7 z^2/810 + z^4/270)/lam
@@ -10,8 +10,8 @@ The first three orders are the known expansion of the continuous inverse of the 
 (Giles, "Algorithm 955", ACM TOMS 42(1) 2016, Q_N1).  This script
   1. recovers the next two orders asymptotically (large lam) from the exact jump points
      z_k = Phi^-1(F(k; lam)) -> Q = k+1, as a check of the expansion's form, and
-  2. fits a/b by weighted least squares on the jump points for lam in [4, 32], which is what
-     the kernel uses (an asymptotic series is not optimal at lam ~ 4), and
+  2. fits a/b by weighted least squares on the jump points for lam in [2, 32], which is what
+     the kernel uses (an asymptotic series is not optimal at lam ~ 2-4), and
   3. prints the sup-CDF error and the chi-square non-centrality per draw of floor(Q(z))
      against the exact Poisson law.
 
@@ -44,7 +44,7 @@ def jump_points(lam, zmax=5.5):
     return z[m], (ks + 1)[m].astype(float)
 
 
-def fit(lams=(4, 4.5, 5, 5.5, 6, 7, 8, 9, 10, 12, 14, 16, 20, 25, 32)):
+def fit(lams=(2, 2.25, 2.5, 2.75, 3, 3.5, 4, 4.5, 5, 5.5, 6, 7, 8, 9, 10, 12, 14, 16, 20, 25, 32)):
     Z, R, L, Wt = [], [], [], []
     for lam in lams:
         z, q = jump_points(lam)
@@ -76,7 +76,7 @@ def main():
     print("fitted a1,a3,a5 =", ", ".join(f"{x:.8f}" for x in a))
     print("fitted b0,b2,b4,b6 =", ", ".join(f"{x:.8f}" for x in b))
     print(f"{'lam':>7} {'sup-CDF 3 orders':>18} {'sup-CDF 5 orders':>18} {'chi2/draw (5)':>15}")
-    for lam in (3, 4, 5, 6, 8, 10, 16, 32, 100, 1000, 10000):
+    for lam in (2, 2.5, 3, 4, 5, 6, 8, 10, 16, 32, 100, 1000, 10000):
         e3, _ = law_error(lam, q3)
         e5, c5 = law_error(lam, lambda z, l: q5(z, l, a, b))
         print(f"{lam:7g} {e3:18.2e} {e5:18.2e} {c5:15.1e}")

@@ -68,8 +68,8 @@ def test_rejection_abort_semantics(vax):
     assert np.allclose(s, [1 - (a + b) for a, b, *_ in p], rtol=0, atol=0)
 
 
-@pytest.mark.parametrize("lam", [0.0, 1e-3, 0.5, 3.0, 9.999, 10.0, 10.5, 16.0, 63.0, 300.0, 2857.0,
-                                 1e4, 1e5])
+@pytest.mark.parametrize("lam", [0.0, 1e-3, 0.5, 1.999, 2.0, 2.5, 3.0, 4.0, 9.999, 10.0, 10.5, 16.0, 63.0,
+                                 300.0, 2857.0, 1e4, 1e5])
 def test_poisson_sampler_law(ctx, lam):
     """Chi-square goodness of fit of the device sampler against the exact Poisson pmf."""
     n = 2_000_000
