@@ -45,8 +45,8 @@ WIDE_DATES = dict(start_date="2020-12-15", end_date="2025-12-14")
 WIDE_T = 1826
 BYTES_PER_SAMPLE_WEEK = 112.0   # 4 int32 counts per sample-day if materialised
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-# from profiles/r01_fold_vh_ncu_summary.txt (ncu --set full of this kernel, this workload, 1e6 samples)
-NCU_WARP_INST_PER_WARP_DAY = 210.1   # smsp__inst_executed.sum / (samples*days/32)
+# from profiles/r01_fold_vi_ncu_summary.txt (ncu --set full of this kernel, this workload, 1e6 samples)
+NCU_WARP_INST_PER_WARP_DAY = 198.5   # smsp__inst_executed.sum / (samples*days/32)
 NCU_DRAM_BYTES_PER_LAUNCH = 3.46e7   # dram__bytes_read.sum + dram__bytes_write.sum
 N_SM, SCHEDULERS_PER_SM = 148, 4
 

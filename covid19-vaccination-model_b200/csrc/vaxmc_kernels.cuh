@@ -102,6 +102,15 @@ __device__ __forceinline__ float fast_rsqrt(float x) { float y; asm("rsqrt.appro
 __device__ __forceinline__ float fast_sin(float x) { float y; asm("sin.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_cos(float x) { float y; asm("cos.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// Packed fp32x2 arithmetic (sm_100: FFMA2 / FMUL2 do two lanes' worth of work in ONE issue slot;
+// the stepper is issue-bound with the FMA pipes at ~40 %, so packing trades idle pipe for slots).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &a, float &b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 splat2(float a) { return pack2(a, a); }
+
 // Two independent N(0,1) from two words (Box-Muller).  u1 in (0,1], angle in [-pi,pi).
 __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, float &z0, float &z1)
 {
@@ -155,6 +164,50 @@ __device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
     const float tail = fmaf(w1, fmaf(w1, fmaf(w1, fmaf(w1, c4, c3), c2), c1), c0);
     // lam + s z + tail in fp32: at lam = 1e5 one ulp is 0.008, i.e. a 1e-5 shift of the CDF --
     // below the expansion's own error; rounding to nearest keeps it unbiased
+    int x = max(__float2int_rd(fmaf(s, z, lam) + tail), 0);
+    if (lam < POISSON_INV_MAX) {
+        x = 0;
+        if (lam > 0.0f) {
+            const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
+            float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
+            while (u >= cdf && x < 40) {
+                ++x;
+                p *= lam * c_rcp[x];
+                cdf += p;
+            }
+        }
+    }
+    return x;
+}
+
+// The z-only part of the expansion for BOTH draws of a day at once (packed fp32x2):
+// c0..c4 of  Q = lam + s z + c0 + w (c1 + w (c2 + w (c3 + w c4))),  w = lam^-1/2.
+struct CFCoef { f32x2 c0, c1, c2, c3, c4; };
+
+__device__ __forceinline__ CFCoef cf_coefficients(float z1, float z2)
+{
+    const f32x2 z = pack2(z1, z2), z2p = mul2(z, z);
+    const f32x2 zc = pack2(fminf(fmaxf(z1, -5.0f), 5.0f), fminf(fmaxf(z2, -5.0f), 5.0f)), zc2 = mul2(zc, zc);
+    CFCoef c;
+    c.c0 = fma2(z2p, splat2(0.16666667f), splat2(0.33333334f));
+    c.c1 = mul2(z, fma2(z2p, splat2(-0.013888889f), splat2(-0.027777778f)));
+    c.c2 = fma2(z2p, fma2(z2p, splat2(0.0037037036f), splat2(0.0086419750f)), splat2(-0.019753087f));
+    c.c3 = mul2(zc, fma2(zc2, fma2(zc2, splat2(CF_A5), splat2(CF_A3)), splat2(CF_A1)));
+    c.c4 = fma2(zc2, fma2(zc2, fma2(zc2, splat2(CF_B6), splat2(CF_B4)), splat2(CF_B2)), splat2(CF_B0));
+    return c;
+}
+
+// poisson_draw with the z-polynomials already evaluated (WHICH = 0: first draw of the pair)
+template <int WHICH>
+__device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &c, uint32_t w)
+{
+    float a0, b0, a1, b1, a2, b2, a3, b3, a4, b4;
+    unpack2(c.c0, a0, b0); unpack2(c.c1, a1, b1); unpack2(c.c2, a2, b2);
+    unpack2(c.c3, a3, b3); unpack2(c.c4, a4, b4);
+    const float c0 = WHICH ? b0 : a0, c1 = WHICH ? b1 : a1, c2 = WHICH ? b2 : a2, c3 = WHICH ? b3 : a3,
+                c4 = WHICH ? b4 : a4;
+    const float w1 = fast_rsqrt(lam), s = lam * w1;
+    const float tail = fmaf(w1, fmaf(w1, fmaf(w1, fmaf(w1, c4, c3), c2), c1), c0);
     int x = max(__float2int_rd(fmaf(s, z, lam) + tail), 0);
     if (lam < POISSON_INV_MAX) {
         x = 0;
@@ -487,16 +540,17 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                 const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)day, TAG_DAY, a.keys);
                 float z1, z2;
                 normal_pair(r.x, r.y, z1, z2);
+                const CFCoef cf = cf_coefficients(z1, z2);
                 // ---- vaccination draw, model.py:102-112
                 const float lam1 = (float)n_wait * ((float)stock * c1);
                 int dv = EXACT ? poisson_draw_exact(lam1, r.z, s_lo, s_hi, (uint32_t)day, 0u, a.keys)
-                               : poisson_draw(lam1, z1, r.z);
+                               : poisson_draw_c<0>(lam1, z1, cf, r.z);
                 dv = min(dv, min(stock, n_wait));
                 n_vacc += dv; n_wait -= dv; stock -= dv;
                 // ---- conversion draw, model.py:115-120
                 const float lam2 = (float)n_agn * ((float)n_vacc * c2);
                 int da = EXACT ? poisson_draw_exact(lam2, r.w, s_lo, s_hi, (uint32_t)day, 1u, a.keys)
-                               : poisson_draw(lam2, z2, r.w);
+                               : poisson_draw_c<1>(lam2, z2, cf, r.w);
                 da = min(da, n_agn);
                 n_agn -= da; n_wait += da;
                 // ---- recording, model.py:124-127 and the weekly series :196-214
