@@ -149,37 +149,6 @@ constexpr float POISSON_INV_MAX = 2.0f;
 constexpr float CF_A1 = 0.01865529f, CF_A3 = 0.00004626f, CF_A5 = -0.00184102f;
 constexpr float CF_B0 = 0.00100592f, CF_B2 = -0.01903893f, CF_B4 = 0.00285482f, CF_B6 = 0.00029421f;
 
-__device__ __forceinline__ int poisson_draw(float lam, float z, uint32_t w)
-{
-    // Horner in w = lam^-1/2:  Q = lam + s z + c0 + w (c1 + w (c2 + w (c3 + w c4)))
-    const float w1 = fast_rsqrt(lam), s = lam * w1, z2 = z * z;
-    // the two fitted orders only matter for small lam; evaluate them at |z| <= 5 so that the
-    // odd/even degree-5/6 polynomials cannot bend Q back in the far tails
-    const float zc = fminf(fmaxf(z, -5.0f), 5.0f), zc2 = zc * zc;
-    const float c0 = fmaf(z2, 0.16666667f, 0.33333334f);
-    const float c1 = z * fmaf(z2, -0.013888889f, -0.027777778f);
-    const float c2 = fmaf(z2, fmaf(z2, 0.0037037036f, 0.0086419750f), -0.019753087f);
-    const float c3 = zc * fmaf(zc2, fmaf(zc2, CF_A5, CF_A3), CF_A1);
-    const float c4 = fmaf(zc2, fmaf(zc2, fmaf(zc2, CF_B6, CF_B4), CF_B2), CF_B0);
-    const float tail = fmaf(w1, fmaf(w1, fmaf(w1, fmaf(w1, c4, c3), c2), c1), c0);
-    // lam + s z + tail in fp32: at lam = 1e5 one ulp is 0.008, i.e. a 1e-5 shift of the CDF --
-    // below the expansion's own error; rounding to nearest keeps it unbiased
-    int x = max(__float2int_rd(fmaf(s, z, lam) + tail), 0);
-    if (lam < POISSON_INV_MAX) {
-        x = 0;
-        if (lam > 0.0f) {
-            const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
-            float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
-            while (u >= cdf && x < 40) {
-                ++x;
-                p *= lam * c_rcp[x];
-                cdf += p;
-            }
-        }
-    }
-    return x;
-}
-
 // The z-only part of the expansion for BOTH draws of a day at once (packed fp32x2):
 // c0..c4 of  Q = lam + s z + c0 + w (c1 + w (c2 + w (c3 + w c4))),  w = lam^-1/2.
 struct CFCoef { f32x2 c0, c1, c2, c3, c4; };
@@ -197,7 +166,8 @@ __device__ __forceinline__ CFCoef cf_coefficients(float z1, float z2)
     return c;
 }
 
-// poisson_draw with the z-polynomials already evaluated (WHICH = 0: first draw of the pair)
+// The Poisson variate of regime table above, given the pair's coefficients (WHICH = 0: first
+// draw of the day, 1: second).
 template <int WHICH>
 __device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &c, uint32_t w)
 {
@@ -230,7 +200,7 @@ __device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &
 // generating Poisson random variables", 1993 -- the algorithm numpy's legacy poisson uses).
 // The acceptance test is evaluated in fp64 (k*log(lam) - lgamma(k+1) cancels catastrophically
 // in fp32 at lam ~ 1e4).  Extra uniforms come from Philox blocks (tag TAG_PTRS, index =
-// 2*(8*day + attempt block) + draw); ~3x slower than poisson_draw, so not the default.
+// 2*(8*day + attempt block) + draw); ~11x slower than the default sampler on the bench job.
 enum : uint32_t { TAG_PTRS = 4 };
 
 __device__ __noinline__ int poisson_draw_exact(float lam, uint32_t w, uint32_t s_lo, uint32_t s_hi,
@@ -1016,7 +986,9 @@ __global__ void vx_test_poisson_kernel(float lam, int64_t n, uint64_t seed, int3
         out[i] = poisson_draw_exact(lam, r.z, (uint32_t)i, (uint32_t)(i >> 32), 3u, 0u, K);
         return;
     }
-    out[i] = poisson_draw(lam, (i & 1) ? z2 : z1, (i & 1) ? r.w : r.z);
+    // the stepper's own code path: packed coefficients for the pair, first / second draw by parity
+    const CFCoef cf = cf_coefficients(z1, z2);
+    out[i] = (i & 1) ? poisson_draw_c<1>(lam, z2, cf, r.w) : poisson_draw_c<0>(lam, z1, cf, r.z);
 }
 
 __global__ void vx_test_normal_kernel(int64_t n, uint64_t seed, float *out)
