@@ -127,7 +127,9 @@ int vx_run_params(vx_ctx *ctx, const vx_config *cfg, const double *params, vx_re
  * (model.py:275-300); params_out host [count][6]; p_soft_no_out host [count] or NULL.     */
 int vx_sample_params(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t count,
                      double *params_out, double *p_soft_no_out);
-/* Raw integer rows of samples [first, first+count) in bounds mode: host int32 [R][count]. */
+/* Raw integer rows of samples [first, first+count) in bounds mode: host int32 [R][count] --
+ * the integers behind what run_single_realization records (model.py:124-127) and run_sampling
+ * stacks (model.py:193), before the float scaling.                                          */
 int vx_dump_counts(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t count,
                    int32_t *counts_out);
 /* Expected-value trajectories of explicit parameter tuples, host double [4][n][T] in the
@@ -136,6 +138,8 @@ int vx_expected_series(vx_ctx *ctx, const vx_config *cfg, const double *params, 
                        double *series_out);
 
 /* ---- staged job: one shard of the global sample range per GPU (multi-GPU path) ----
+ * The sample loop of run_sampling (model.py:176-189) split over ranks by global sample id;
+ * the per-date reduction (model.py:216-228) happens after the integer slab is merged.
  *   vx_job_begin(cfg, shard_first, shard_count)
  *   vx_job_param_stats(stats[4])        this shard's rejection count / p_soft_no moments
  *   [vx_job_set_param_stats(stats[4])]  OPTIONAL: hand back stats summed over ranks by the
@@ -172,7 +176,9 @@ double vx_host_count_to_value(int series, int64_t count, int64_t N);
 int32_t vx_host_weeks(int32_t T);
 int64_t vx_host_rows(int32_t T);
 
-/* ---- device self-tests of the building blocks (used by tests/, tiny launches) ----- */
+/* ---- device self-tests of the building blocks (used by tests/, tiny launches) -----
+ * vx_test_poisson draws with the stepper's own sampler (the np.random.poisson calls of
+ * model.py:104,116); vx_test_select is the order-statistics step of np.quantile (model.py:220). */
 int vx_test_philox(vx_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int vx_test_poisson(vx_ctx *ctx, double lam, int64_t n, uint64_t seed, int32_t *out_host);
 int vx_test_normal(vx_ctx *ctx, int64_t n, uint64_t seed, float *out_host);
