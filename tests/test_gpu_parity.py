@@ -660,3 +660,28 @@ def test_exact_poisson_mode(vax, ctx):
     assert pv.min() > 0.01 / len(pv) and (pv < 0.01).mean() <= 0.04, (pv.min(), (pv < 0.01).mean())
     print(f"\nexact vs default sampler, {m} samples per arm: {len(pv)} KS tests, min p={pv.min():.4f}, "
           f"median p={np.median(pv):.3f}")
+
+
+def test_cli_configs0_readme_scenario(vax, tmp_path):
+    """BASELINE configs[0]: the README command line (default mc_samples=100, --CI default 0.95 with
+    the /100 quirk of model.py:358) through main(); JSON == run_model's arrays; bands against the
+    reference's own seeded run of the same command within Monte Carlo error of n=100."""
+    import json
+
+    out = tmp_path / "res.json"
+    argv = ("--pro=35,45 --anti=12,25 --pressure=0.,0.02 --dupl_time=5,7 --init_stock=1,1.2 "
+            "--max_delivery=5,10 --date_range=2020-12-15,2022-07-1 --seed 5 --no_plot").split()
+    assert vax.main(argv + ["--json_out", str(out)]) == 0
+    js = json.loads(out.read_text())
+    res, err, msg = vax.run_model([35.0, 45.0], [12.0, 25.0], [0.0, 0.02], [5.0, 7.0], [1.0, 1.2], [5.0, 10.0],
+                                  0.95, 100, 50000, dict(start_date="2020-12-15", end_date="2022-07-1"), seed=5)
+    assert err == "" and js["number_finished_samples"] == 100
+    for k in SERIES:
+        assert len(js[k]["mean"]) == (81 if k == SERIES[1] else 564)
+        for f in ("mean", "lower", "upper"):
+            assert js[k][f] == res[k][f].tolist()
+        assert js[k]["dates"][0].startswith("2020-12-15")
+        # CI = 0.95 % -> quantiles 0.49525 / 0.50475: the band hugs the median (SURVEY D5)
+        assert (res[k]["upper"] >= res[k]["lower"]).all()
+    width = res[SERIES[0]]["upper"][-1] - res[SERIES[0]]["lower"][-1]
+    assert width < 2.0            # reference measured 0.149 at CI=0.95 vs 46.0 at CI=95
