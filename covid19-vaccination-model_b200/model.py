@@ -118,19 +118,9 @@ def _agnostics_message(soft_mean_frac: float, soft_std_frac: float) -> str:
 
 # --------------------------------------------------------------------- the boundary
 def run_model(
-    # populatio parameters
-    p_pro_bounds,
-    p_anti_bounds,
-    pressure_bounds,
-    # vaccinations parameters
-    tau_bounds,
-    nv_0_bounds,
-    nv_max_bounds,
-    # samping
-    CI,
-    n_rep,
-    N,
-    date_range,
+    p_pro_bounds, p_anti_bounds, pressure_bounds,      # population: % pro, % anti, pressure
+    tau_bounds, nv_0_bounds, nv_max_bounds,            # supply: doubling time, first and max delivery (%)
+    CI, n_rep, N, date_range,                          # CI in percent, samples, population, dates
     max_running_time=None,
     *,
     seed=None,
