@@ -111,7 +111,7 @@ struct vx_ctx {
     int64_t launches = 0;
     Job *job = nullptr;
     // options
-    int64_t max_bins = 65536;
+    int64_t max_bins = 262144;            // 2^18: keeps N = 1e6 deliveries (1.5 % of ~4e6 doses) at unit resolution in one pass
     int64_t chunk_samples = 1 << 20;
     double pilot_sigmas = 6.0;
     int64_t use_pilot = 1;

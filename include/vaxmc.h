@@ -102,7 +102,7 @@ void vx_destroy(vx_ctx *ctx);
 const char *vx_last_error(vx_ctx *ctx); /* ctx may be NULL: last error of vx_create  */
 const char *vx_version(void);
 int vx_device_count(void);              /* 0 when no CUDA device is usable            */
-/* tuning knobs (mainly for tests): "max_bins" (bins per window, default 65536),
+/* tuning knobs (mainly for tests): "max_bins" (bins per window, default 262144),
  * "pilot_sigmas" (half-width of the pilot bracket in rank sigmas, default 6),
  * "use_pilot" (0: start from the coarse full-range windows), "sort_samples" (0: fold the
  * shard in id order instead of pressure-bucket order; same integers either way), "chunk_samples"

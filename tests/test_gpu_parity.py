@@ -401,7 +401,7 @@ def test_streamed_refinement_paths(vax, ctx):
         ctx.set_option("use_pilot", 0)
         b = _run(vax, ctx, bounds, n, 5, direct_max=1)
         assert b.c.n_passes >= 3 and _same(direct, b)
-        ctx.set_option("max_bins", 65536)
+        ctx.set_option("max_bins", 262144)
         c = _run(vax, ctx, bounds, n, 5, direct_max=1)
         assert c.c.n_passes >= 2 and _same(direct, c)
         ctx.set_option("use_pilot", 1)
@@ -409,7 +409,7 @@ def test_streamed_refinement_paths(vax, ctx):
         d = _run(vax, ctx, bounds, n, 5, direct_max=1, pilot=2048)
         assert d.c.n_passes >= 2 and _same(direct, d)
     finally:
-        ctx.set_option("max_bins", 65536); ctx.set_option("use_pilot", 1); ctx.set_option("pilot_sigmas", 6.0)
+        ctx.set_option("max_bins", 262144); ctx.set_option("use_pilot", 1); ctx.set_option("pilot_sigmas", 6.0)
     try:                                      # regime sort on/off: same integers either way
         ctx.set_option("sort_samples", 0)
         e = _run(vax, ctx, bounds, n, 5, direct_max=1, pilot=4096)
