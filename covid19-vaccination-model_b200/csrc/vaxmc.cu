@@ -469,39 +469,21 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
 }
 
 // Pilot size.  The pilot is replicated on every rank and its stepper is latency-bound (one
-// 564-day dependency chain per warp, ~0.4 ms however few samples), the select pass scales
-// with n_p, and the window width -- hence the slab the ranks all-reduce -- with n_p^-1/2.
-// The fold's slow path costs ~1 % of the fold at n_p = 32768 (windows hold ~1 % of the mass),
-// so a bigger pilot buys nothing; it only has to be big enough that the +-6 sigma bracket of
-// the outer quantile stays inside the pilot sample: n_p * q_tail >~ 64.
-// Counting sort of samples [first, first+count) by pressure bucket into d_perm (local ids).
-int launch_regime_sort(vx_ctx *ctx, Job *j, int64_t first, int64_t count, cudaStream_t st, int32_t **perm_out)
-{
-    void *p_ = nullptr;
-    int rc = pool_get(ctx, SLOT_PERM, sizeof(int32_t) * count, &p_);
-    if (rc) return rc;
-    int32_t *d_perm = (int32_t *)p_;
-    rc = pool_get(ctx, SLOT_SORT, sizeof(uint32_t) * SORT_BUCKETS, &p_);
-    if (rc) return rc;
-    uint32_t *d_cnt = (uint32_t *)p_;
-    const unsigned sgrid = (unsigned)((count + 255) / 256);
-    CK(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * SORT_BUCKETS, st));
-    vx_bucket_count_kernel<<<sgrid, 256, 0, st>>>(j->cfg.seed, first, count, d_cnt);
-    CKL();
-    vx_bucket_scan_kernel<<<1, SORT_BUCKETS, 0, st>>>(d_cnt);
-    CKL();
-    vx_bucket_scatter_kernel<<<sgrid, 256, 0, st>>>(j->cfg.seed, first, count, d_cnt, d_perm);
-    CKL();
-    *perm_out = d_perm;
-    return VX_OK;
-}
-
-int64_t default_pilot(double q_lo, double q_hi)
+// 564-day dependency chain per warp, ~0.4 ms however few samples) plus ~1e-5 ms per sample
+// (stepper + select); the window width -- hence the fold's slow path and the slab the ranks
+// all-reduce -- goes with n_p^-1/2.  Measured on B200 (USA shape): fold_ms(n_p) = F (1 + 4.1
+// n_p^-1/2) with F = 4.1 ms per 1e6 samples, so the cost  0.5 + 1e-5 n_p + fold_ms  is minimal
+// at n_p = (0.84 n)^(2/3): 16384 at 1e6 samples (measured optimum), 32768 at 8e6 (measured),
+// capped at 2^18.  Independently the +-6 sigma bracket of the outer quantile has to stay
+// inside the pilot sample: n_p * q_tail >~ 64.
+int64_t default_pilot(double q_lo, double q_hi, int64_t n)
 {
     double tail = std::min(std::min(q_lo, 1.0 - q_lo), std::min(q_hi, 1.0 - q_hi));
     tail = std::max(tail, 1e-9);
     int64_t p = 16384;
     while ((double)p * tail < 64.0 && p < ((int64_t)1 << 20)) p <<= 1;
+    const double opt = std::pow(0.84 * (double)n, 2.0 / 3.0);
+    while ((double)(2 * p) <= opt && p < ((int64_t)1 << 18)) p <<= 1;
     return p;
 }
 
@@ -792,7 +774,7 @@ int vx_job_pilot(vx_ctx *ctx)
         j->n_pilot = 0;
         return plan_windows(ctx, false);
     }
-    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(j->cfg.q_lo, j->cfg.q_hi));
+    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(j->cfg.q_lo, j->cfg.q_hi, n));
     j->n_pilot = np;
     if (!j->direct && ctx->sort_samples && !j->explicit_params && !(j->cfg.max_running_time > 0.0)) {
         // the part of the shard the stepper will fold (the pilot's own samples come from its matrix):
