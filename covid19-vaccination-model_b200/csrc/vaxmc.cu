@@ -468,6 +468,28 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
     return VX_OK;
 }
 
+// Counting sort of samples [first, first+count) by pressure bucket into d_perm (local ids).
+int launch_regime_sort(vx_ctx *ctx, Job *j, int64_t first, int64_t count, cudaStream_t st, int32_t **perm_out)
+{
+    void *p_ = nullptr;
+    int rc = pool_get(ctx, SLOT_PERM, sizeof(int32_t) * count, &p_);
+    if (rc) return rc;
+    int32_t *d_perm = (int32_t *)p_;
+    rc = pool_get(ctx, SLOT_SORT, sizeof(uint32_t) * SORT_BUCKETS, &p_);
+    if (rc) return rc;
+    uint32_t *d_cnt = (uint32_t *)p_;
+    const unsigned sgrid = (unsigned)((count + 255) / 256);
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(uint32_t) * SORT_BUCKETS, st));
+    vx_bucket_count_kernel<<<sgrid, 256, 0, st>>>(j->cfg.seed, first, count, d_cnt);
+    CKL();
+    vx_bucket_scan_kernel<<<1, SORT_BUCKETS, 0, st>>>(d_cnt);
+    CKL();
+    vx_bucket_scatter_kernel<<<sgrid, 256, 0, st>>>(j->cfg.seed, first, count, d_cnt, d_perm);
+    CKL();
+    *perm_out = d_perm;
+    return VX_OK;
+}
+
 // Pilot size.  The pilot is replicated on every rank and its stepper is latency-bound (one
 // 564-day dependency chain per warp, ~0.4 ms however few samples) plus ~1e-5 ms per sample
 // (stepper + select); the window width -- hence the fold's slow path and the slab the ranks
