@@ -123,12 +123,15 @@ def load() -> C.CDLL:
         path = _build.LIB
         if _build.needs_build():
             try:
-                path = _build.build()
-            except Exception as e:  # stale .so on a box without nvcc: use it, else fail loudly
+                nvcc = _build.find_nvcc()
+            except RuntimeError as e:   # a box without nvcc: the shipped in-tree .so is all there is
+                nvcc = None
                 if not os.path.exists(path):
                     raise RuntimeError(
                         "libvaxmc.so is missing and could not be built; this package has no "
                         f"CPU fallback ({e})") from e
+            if nvcc is not None:
+                path = _build.build()   # a compile error must surface, never a stale library
         L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the library does not export it
