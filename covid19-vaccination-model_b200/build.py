@@ -39,10 +39,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     extra = os.environ.get("VAXMC_NVCC_EXTRA", "").split()
-    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", LIB, SRC]
+    # build next to the target and rename: ranks of one torchrun job that all find the library
+    # stale may compile concurrently, and none of them may ever load a half-written file
+    tmp = f"{LIB}.tmp{os.getpid()}"
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, "-o", tmp, SRC]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB)
     if verbose:
         print(proc.stdout + proc.stderr)
     return LIB
