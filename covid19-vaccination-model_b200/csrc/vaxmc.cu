@@ -72,6 +72,7 @@ struct Job {
     Win *d_wins = nullptr;
     unsigned long long *d_acc = nullptr;
     int64_t acc_words = 0, acc_cap = 0;
+    int bins64 = 0;                       // 64-bit histogram bins (global n >= 2^32), else 32-bit
     int *d_tgt = nullptr;                 // [R][2][2] which wanted rank each window serves
     long long *d_res = nullptr;
     // host state of the streaming job
@@ -405,7 +406,7 @@ int plan_windows(vx_ctx *ctx, bool from_pilot)
             off += wp.w.len >> wp.w.shift;
         }
     }
-    const int64_t words = ACC_HDR + 3 * R + (int64_t)off;
+    const int64_t words = ACC_HDR + 3 * R + (j->bins64 ? (int64_t)off : (int64_t)((off + 1) / 2));
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_ACC, sizeof(unsigned long long) * words, &p_); if (rc_) return rc_; j->d_acc = (unsigned long long *)p_; }
     j->acc_words = words;
     std::vector<Win> hw(R * 2);
@@ -688,6 +689,7 @@ static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_fir
     j->W = (cfg->T + 6) / 7;
     j->R = 2 * (int64_t)j->T + 2 * (int64_t)j->W;
     j->explicit_params = h_params != nullptr;
+    j->bins64 = cfg->n_samples >= ((int64_t)1 << 32) ? 1 : 0;
     const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 65536;   // crossover of direct vs pilot+fold on B200 (USA shape)
     j->direct = (cfg->mode == VX_MODE_EXPECTED) || cfg->n_samples <= dmax;
     j->t_begin = std::chrono::steady_clock::now();
@@ -891,7 +893,7 @@ int vx_job_accumulate(vx_ctx *ctx)
     const int64_t pil_hi = (j->d_dump && j->n_pilot > 0) ? std::min(hi, j->n_pilot) : lo;
     int64_t done = 0;
     if (pil_hi > lo) {
-        vx_fold_matrix_kernel<<<(unsigned)j->R, 256, 0, ctx->stream>>>(j->d_dump, j->n_pilot, lo, pil_hi, j->d_wins, j->d_acc, (int)j->R);
+        vx_fold_matrix_kernel<<<(unsigned)j->R, 256, 0, ctx->stream>>>(j->d_dump, j->n_pilot, lo, pil_hi, j->d_wins, j->d_acc, (int)j->R, j->bins64);
         CKL();
         done = pil_hi - lo;
     }
@@ -901,6 +903,7 @@ int vx_job_accumulate(vx_ctx *ctx)
                               j->d_params ? j->d_params + 6 * (j->shard_first + done) : nullptr);
         a.wins = j->d_wins;
         a.acc = j->d_acc;
+        a.bins64 = j->bins64;
         if (j->d_perm && j->perm_first == a.first && j->perm_count == cnt) {
             CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));
             a.perm = j->d_perm;
@@ -952,7 +955,7 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
         const int64_t R = j->R;
         unsigned long long hdr[ACC_HDR];
         const int64_t warps = 2 * R, grid = (warps * 32 + 255) / 256;
-        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R, j->cfg.q_lo, j->cfg.q_hi);
+        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R, j->cfg.q_lo, j->cfg.q_hi, j->bins64);
         CKL();
         std::vector<long long> hres(R * 4);
         std::vector<long long> sums(R);

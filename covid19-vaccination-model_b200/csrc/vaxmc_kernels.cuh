@@ -26,10 +26,12 @@ constexpr uint32_t PHILOX_M0 = 0xD2511F53u, PHILOX_M1 = 0xCD9E8D57u;
 constexpr uint32_t PHILOX_W0 = 0x9E3779B9u, PHILOX_W1 = 0xBB67AE85u;
 
 enum : uint32_t {
-    TAG_DAY = 0,     // index = day: 4 words -> Box-Muller pair + 2 inversion uniforms
+    TAG_DAY = 0,     // index = day >> 1: 4 words -> two Box-Muller pairs = the 2 x 2 normals of two days
     TAG_PRO_ANTI = 1,// index = rejection attempt: p_pro, p_anti (2 x 53-bit)
     TAG_PARAMS_A = 2,// pressure, tau
     TAG_PARAMS_B = 3,// nv_0, nv_max
+    TAG_PTRS = 4,    // exact-Poisson validation mode: PTRS attempts
+    TAG_INV = 5,     // exact-Poisson validation mode: index = day, inversion uniforms (words 0,1)
     TAG_TEST = 7
 };
 
@@ -125,9 +127,28 @@ __device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, float &z0,
 // 1/k for the inversion recurrence p_k = p_{k-1} * lam / k
 __constant__ float c_rcp[72];
 
-// Poisson(lam) variate.
+// Phi(z) in fp32 (Abramowitz & Stegun 26.2.17, |error| < 7.5e-8 plus fp32 rounding): the uniform
+// of the inversion regime.  z ~ N(0,1) makes Phi(z) ~ U(0,1), and it is monotone in z like the
+// expansion below, so one normal per draw serves both regimes and a Philox block (4 words = two
+// Box-Muller pairs) covers TWO days.
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ float normal_cdf(float z)
+{
+    const float x = fabsf(z);
+    const float t = fast_rcp(fmaf(0.2316419f, x, 1.0f));
+    float poly = fmaf(t, 1.330274429f, -1.821255978f);
+    poly = fmaf(t, poly, 1.781477937f);
+    poly = fmaf(t, poly, -0.356563782f);
+    poly = fmaf(t, poly, 0.319381530f);
+    // phi(x) = exp(-x^2/2)/sqrt(2 pi) = 2^(-x^2 log2(e)/2) / sqrt(2 pi)
+    const float tail = (0.3989422804f * fast_ex2(x * x * -0.7213475204f)) * (t * poly);
+    return z > 0.0f ? 1.0f - tail : tail;
+}
+
+// Poisson(lam) variate from ONE standard normal z.
 //   lam == 0          -> 0 (numpy returns 0 without consuming the stream, model.py:104,116)
-//   0 < lam < 2       -> exact inversion by sequential search with one uniform (word w)
+//   0 < lam < 2       -> exact inversion by sequential search on the uniform Phi(z)
 //   lam >= 2          -> floor of the continuous inverse Q(z) of the Poisson CDF expanded
 //                        around the normal quantile z (Cornish-Fisher with the lattice
 //                        correction; the first three orders are Giles' Q_N1, ACM TOMS 42(1),
@@ -166,10 +187,24 @@ __device__ __forceinline__ CFCoef cf_coefficients(float z1, float z2)
     return c;
 }
 
-// The Poisson variate of regime table above, given the pair's coefficients (WHICH = 0: first
+// Sequential-search inversion on u in [0,1): smallest x with u < F(x; lam), 0 < lam < 2.
+__device__ __forceinline__ int poisson_invert(float lam, float u, int kmax)
+{
+    u = fminf(u, 0.99999994f);
+    float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
+    int x = 0;
+    while (u >= cdf && x < kmax) {
+        ++x;
+        p *= lam * c_rcp[x];
+        cdf += p;
+    }
+    return x;
+}
+
+// The Poisson variate of the regime table above, given the pair's coefficients (WHICH = 0: first
 // draw of the day, 1: second).
 template <int WHICH>
-__device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &c, uint32_t w)
+__device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &c)
 {
     float a0, b0, a1, b1, a2, b2, a3, b3, a4, b4;
     unpack2(c.c0, a0, b0); unpack2(c.c1, a1, b1); unpack2(c.c2, a2, b2);
@@ -181,15 +216,7 @@ __device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &
     int x = max(__float2int_rd(fmaf(s, z, lam) + tail), 0);
     if (lam < POISSON_INV_MAX) {
         x = 0;
-        if (lam > 0.0f) {
-            const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
-            float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
-            while (u >= cdf && x < 40) {
-                ++x;
-                p *= lam * c_rcp[x];
-                cdf += p;
-            }
-        }
+        if (lam > 0.0f) x = poisson_invert(lam, normal_cdf(z), 40);
     }
     return x;
 }
@@ -199,20 +226,17 @@ __device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &
 // lam >= 10 Hoermann's PTRS transformed rejection ("The transformed rejection method for
 // generating Poisson random variables", 1993 -- the algorithm numpy's legacy poisson uses).
 // The acceptance test is evaluated in fp64 (k*log(lam) - lgamma(k+1) cancels catastrophically
-// in fp32 at lam ~ 1e4).  Extra uniforms come from Philox blocks (tag TAG_PTRS, index =
-// 2*(8*day + attempt block) + draw); ~11x slower than the default sampler on the bench job.
-enum : uint32_t { TAG_PTRS = 4 };
+// in fp32 at lam ~ 1e4).  Its uniforms come from Philox blocks of their own (TAG_INV, index = day,
+// for the inversion; TAG_PTRS, index = 2*(8*day + attempt block) + draw, for the rejection loop);
+// ~11x slower than the default sampler on the bench job.
 
-__device__ __noinline__ int poisson_draw_exact(float lam, uint32_t w, uint32_t s_lo, uint32_t s_hi,
+__device__ __noinline__ int poisson_draw_exact(float lam, uint32_t s_lo, uint32_t s_hi,
                                                uint32_t day, uint32_t which, const PhiloxKeys &K)
 {
     if (!(lam > 0.0f)) return 0;
     if (lam < 10.0f) {
-        const float u = fminf((float)w * 2.3283064365386963e-10f, 0.99999994f);
-        float p = fast_ex2(lam * -1.4426950408889634f), cdf = p;
-        int x = 0;
-        while (u >= cdf && x < 70) { ++x; p *= lam * c_rcp[x]; cdf += p; }
-        return x;
+        const uint4 r = philox4x32_10(s_lo, s_hi, day, TAG_INV, K);
+        return poisson_invert(lam, (float)(which ? r.y : r.x) * 2.3283064365386963e-10f, 70);
     }
     const double L = (double)lam, slam = sqrt(L), loglam = log(L);
     const double b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
@@ -432,7 +456,31 @@ struct SimArgs {
     const int32_t *perm;    // FOLD: optional order of the local samples (pressure-sorted), or nullptr
     const Win *wins;        // FOLD: [R][2]
     unsigned long long *acc;// FOLD: header(8) | sums[R] | below[R][2] | hist bins
+    int bins64;             // FOLD: histogram bins are 64-bit words (global n >= 2^32), else 32-bit
 };
+
+// One more count in histogram bin `idx` of the slab.  Bins are 32-bit unless the job has 2^32 or
+// more samples: they are packed two per 64-bit slab word and, below 2^32 samples, can never
+// carry into their neighbour, so the ranks still merge the whole slab with ONE int64
+// all-reduce(sum).
+__device__ __forceinline__ void bin_add(unsigned long long *hist, uint32_t idx, int bins64, uint32_t count = 1u)
+{
+    if (bins64) atomicAdd(hist + idx, (unsigned long long)count);
+    else atomicAdd(reinterpret_cast<unsigned int *>(hist) + idx, count);
+}
+
+// The same as a PREDICATED reduction (no branch): the stepper's fold revisits quads of samples in
+// which some value hit a window and tests all eight (value, window) pairs; a branch per pair
+// costs more issue slots than the eight predicated REDs.
+__device__ __forceinline__ void bin_add_if(bool pred, unsigned long long *hist, uint32_t idx, int bins64)
+{
+    if (bins64)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.global.add.u64 [%1], 1;\n\t}"
+                     :: "r"((uint32_t)pred), "l"(hist + idx) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %0, 0;\n\t@q red.global.add.u32 [%1], 1;\n\t}"
+                     :: "r"((uint32_t)pred), "l"(reinterpret_cast<unsigned int *>(hist) + idx) : "memory");
+}
 
 constexpr int ACC_HDR = 8;
 constexpr int WIN_DAYS = 14;       // one warp tile = 2 weeks = 14+14+2+2 = 32 rows
@@ -476,7 +524,7 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
     const double p_agn = 1 - (p.p_pro + p.p_anti);
     int n_wait = (int)(p.p_pro * Nd);
     int n_agn = (int)(p_agn * Nd);
-    int stock = 0, received = 0, n_vacc = 0;
+    int stock = 0, n_vacc = 0;
     const double tau7 = p.tau * 7;
     const double ln2 = 0.6931471805599453;                 // np.log(2)
     const bool monotone = (p.tau > 0.0) && (p.nv0 > 0.0);
@@ -489,66 +537,76 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
     const int T = a.T, W = a.W;
     for (int d0 = 0; d0 < T; d0 += WIN_DAYS) {
         int *tp = tile + lane;                              // this sample's column of the tile
-#pragma unroll 1
-        for (int wk = 0; wk < 2; ++wk) {
-            const int dw = d0 + 7 * wk;
-            if (dw >= T) break;
-            // ---- weekly arrivals, model.py:69, 85-92 (fp64: the truncation must match)
+        const int nd = min(WIN_DAYS, T - d0);               // days in this tile
+        // ---- weekly arrivals, model.py:69, 85-92 (fp64: the truncation must match)
+        auto arrivals = [&](const int day) {
             int arr;
             if (capped) {
                 arr = arr_cap;
             } else {
-                const double g = p.nv0 * exp(ln2 * (double)dw / tau7);
+                const double g = p.nv0 * exp(ln2 * (double)day / tau7);
                 const bool over = p.nvmax < g;              // Python min(g, nv_max)
                 arr = (int)((over ? p.nvmax : g) * Nd);
                 capped = over && monotone;
             }
-            stock += arr; received += arr;
-            const int dend = min(7, T - dw);
-            auto day_step = [&](const int dd) {
-                const int day = dw + dd;
-                const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)day, TAG_DAY, a.keys);
-                float z1, z2;
-                normal_pair(r.x, r.y, z1, z2);
-                const CFCoef cf = cf_coefficients(z1, z2);
-                // ---- vaccination draw, model.py:102-112
-                const float lam1 = (float)n_wait * ((float)stock * c1);
-                int dv = EXACT ? poisson_draw_exact(lam1, r.z, s_lo, s_hi, (uint32_t)day, 0u, a.keys)
-                               : poisson_draw_c<0>(lam1, z1, cf, r.z);
-                dv = min(dv, min(stock, n_wait));
-                n_vacc += dv; n_wait -= dv; stock -= dv;
-                // ---- conversion draw, model.py:115-120
-                const float lam2 = (float)n_agn * ((float)n_vacc * c2);
-                int da = EXACT ? poisson_draw_exact(lam2, r.w, s_lo, s_hi, (uint32_t)day, 1u, a.keys)
-                               : poisson_draw_c<1>(lam2, z2, cf, r.w);
-                da = min(da, n_agn);
-                n_agn -= da; n_wait += da;
-                // ---- recording, model.py:124-127 and the weekly series :196-214
-                if (MODE == SIM_FOLD) {
-                    tp[0] = n_vacc;
-                    tp[14 * TILE_LD] = stock;
-                    tp += TILE_LD;
-                    if (dd == 0) {
-                        tile[(28 + wk) * TILE_LD + lane] = dv + q0;
-                        tile[(30 + wk) * TILE_LD + lane] = received;
-                    }
-                } else if (live) {
-                    const int64_t ld = a.dump_stride;
-                    a.dump[(int64_t)day * ld + local] = n_vacc;
-                    a.dump[((int64_t)T + 2 * W + day) * ld + local] = stock;
-                    if (dd == 0) {
-                        const int k = dw / 7;
-                        a.dump[((int64_t)T + k) * ld + local] = dv + q0;
-                        a.dump[((int64_t)T + W + k) * ld + local] = received;
-                    }
+            stock += arr;                                   // received == n_vacc + stock at all times
+        };
+        // one day of model.py:82-127; (z1, z2) = the day's two normals.  WEEK0: day % 7 == 0
+        // (arrivals already added; the weekly rows are recorded), wk = week slot of the tile
+        auto day_step = [&](const int day, const float z1, const float z2, const bool week0, const int wk) {
+            const CFCoef cf = cf_coefficients(z1, z2);
+            // ---- vaccination draw, model.py:102-112
+            const float lam1 = (float)n_wait * ((float)stock * c1);
+            int dv = EXACT ? poisson_draw_exact(lam1, s_lo, s_hi, (uint32_t)day, 0u, a.keys)
+                           : poisson_draw_c<0>(lam1, z1, cf);
+            dv = min(dv, min(stock, n_wait));
+            n_vacc += dv; n_wait -= dv; stock -= dv;
+            // ---- conversion draw, model.py:115-120
+            const float lam2 = (float)n_agn * ((float)n_vacc * c2);
+            int da = EXACT ? poisson_draw_exact(lam2, s_lo, s_hi, (uint32_t)day, 1u, a.keys)
+                           : poisson_draw_c<1>(lam2, z2, cf);
+            da = min(da, n_agn);
+            n_agn -= da; n_wait += da;
+            // ---- recording, model.py:124-127 and the weekly series :196-214
+            if (MODE == SIM_FOLD) {
+                tp[0] = n_vacc;
+                tp[14 * TILE_LD] = stock;
+                tp += TILE_LD;
+                if (week0) {
+                    tile[(28 + wk) * TILE_LD + lane] = dv + q0;
+                    tile[(30 + wk) * TILE_LD + lane] = n_vacc + stock;
                 }
-                if (dd == 5) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dv; }
-            };
-            // kept rolled on purpose: unrolling the week (compile-time dd, immediate tile offsets)
-            // saves ~10 instructions per day but the 47 KB body misses the instruction cache
-            // and measured 1 % slower on B200
+            } else if (live) {
+                const int64_t ld = a.dump_stride;
+                a.dump[(int64_t)day * ld + local] = n_vacc;
+                a.dump[((int64_t)T + 2 * W + day) * ld + local] = stock;
+                if (week0) {
+                    const int k = day / 7;
+                    a.dump[((int64_t)T + k) * ld + local] = dv + q0;
+                    a.dump[((int64_t)T + W + k) * ld + local] = n_vacc + stock;
+                }
+            }
+            return dv;
+        };
+        // Two days per Philox block (tile days 2pp and 2pp+1): the pair loop is kept rolled (an
+        // unrolled week, ~47 KB, misses the instruction cache and measured 1 % slower); the
+        // events of the week (arrivals at tile days 0 and 7, the delay-line shift at 5 and 12)
+        // are warp-uniform branches on pp.
 #pragma unroll 1
-            for (int dd = 0; dd < dend; ++dd) day_step(dd);
+        for (int pp = 0; 2 * pp < nd; ++pp) {
+            const int dayA = d0 + 2 * pp;
+            const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)dayA >> 1, TAG_DAY, a.keys);
+            float z1, z2;
+            normal_pair(r.x, r.y, z1, z2);
+            if (pp == 0) arrivals(dayA);
+            const int dvA = day_step(dayA, z1, z2, pp == 0, 0);
+            if (pp == 6) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvA; }     // tile day 12 = 5 (mod 7)
+            if (2 * pp + 1 < nd) {
+                normal_pair(r.z, r.w, z1, z2);
+                if (pp == 3) arrivals(dayA + 1);                                // tile day 7
+                const int dvB = day_step(dayA + 1, z1, z2, pp == 3, 1);
+                if (pp == 2) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvB; }  // tile day 5
+            }
         }
         if (MODE == SIM_FOLD) {
             // ---- fold: lane r owns tile row r (one date of one series) over the warp's samples
@@ -563,32 +621,20 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                 const Win wl = a.wins[grow * 2], wh = a.wins[grow * 2 + 1];
                 unsigned long long *hist = a.acc + ACC_HDR + 3 * (int64_t)R;
                 uint32_t sum = 0, clo = 0, chi = 0;
-                uint32_t rb_lo = 0xffffffffu, rc_lo = 0, rb_hi = 0xffffffffu, rc_hi = 0;
                 const int *row = tile + lane * TILE_LD;
-                // in-window values are rare (the windows hold ~1% of the mass): one combined
-                // test per 4 samples, run-length aggregated histogram updates on the slow path
-                auto slow = [&](int v) {
-                    const int dl = v - wl.a, dh = v - wh.a;
-                    if ((uint32_t)dl < wl.len) {
-                        const uint32_t b = (uint32_t)dl >> wl.shift;
-                        if (b != rb_lo) {
-                            if (rc_lo) atomicAdd(hist + wl.off + rb_lo, (unsigned long long)rc_lo);
-                            rb_lo = b; rc_lo = 0;
-                        }
-                        ++rc_lo;
-                    }
-                    if ((uint32_t)dh < wh.len) {
-                        const uint32_t b = (uint32_t)dh >> wh.shift;
-                        if (b != rb_hi) {
-                            if (rc_hi) atomicAdd(hist + wh.off + rb_hi, (unsigned long long)rc_hi);
-                            rb_hi = b; rc_hi = 0;
-                        }
-                        ++rc_hi;
-                    }
+                // a value inside one of the row's two windows: one more count in its bin
+                auto hit = [&](int v) {
+                    const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
+                    bin_add_if(dl < wl.len, hist, wl.off + (dl >> wl.shift), a.bins64);
+                    bin_add_if(dh < wh.len, hist, wh.off + (dh >> wh.shift), a.bins64);
                 };
-                int s = 0;
-#pragma unroll 1
-                for (; s + 4 <= nvalid; s += 4) {
+                // In-window values are rare (the windows hold ~1-3 % of the mass), but with 32
+                // rows in flight SOME lane has one in almost every step: the scan is branch-free
+                // (one combined test per 4 samples sets a bit) and the quads with a hit are
+                // revisited afterwards, so the divergent part runs max-over-lanes(#hit quads)
+                // times per tile (~3) instead of once per step (8).
+                uint32_t hits = 0;
+                auto scan4 = [&](const int s) {
                     const int4 v4 = *reinterpret_cast<const int4 *>(row + s);
                     const int v0 = v4.x, v1 = v4.y, v2 = v4.z, v3 = v4.w;
                     sum += (uint32_t)v0 + (uint32_t)v1 + (uint32_t)v2 + (uint32_t)v3;
@@ -597,17 +643,29 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                     clo += (l0 >> 31) + (l1 >> 31) + (l2 >> 31) + (l3 >> 31);
                     chi += (h0 >> 31) + (h1 >> 31) + (h2 >> 31) + (h3 >> 31);
                     const uint32_t ml = min(min(l0, l1), min(l2, l3)), mh = min(min(h0, h1), min(h2, h3));
-                    if (ml < wl.len || mh < wh.len) { slow(v0); slow(v1); slow(v2); slow(v3); }
+                    if (ml < wl.len || mh < wh.len) hits |= 1u << (s >> 2);
+                };
+                if (nvalid == 32) {
+#pragma unroll
+                    for (int s = 0; s < 32; s += 4) scan4(s);
+                } else {
+                    int s = 0;
+#pragma unroll 1
+                    for (; s + 4 <= nvalid; s += 4) scan4(s);
+                    for (; s < nvalid; ++s) {
+                        const int v = row[s];
+                        sum += (uint32_t)v;
+                        clo += (uint32_t)(v - wl.a) >> 31;
+                        chi += (uint32_t)(v - wh.a) >> 31;
+                        hit(v);
+                    }
                 }
-                for (; s < nvalid; ++s) {
-                    const int v = row[s];
-                    sum += (uint32_t)v;
-                    clo += (uint32_t)(v - wl.a) >> 31;
-                    chi += (uint32_t)(v - wh.a) >> 31;
-                    slow(v);
+                while (hits) {
+                    const int qd = __ffs((int)hits) - 1;
+                    hits &= hits - 1;
+                    const int4 v4 = *reinterpret_cast<const int4 *>(row + 4 * qd);
+                    hit(v4.x); hit(v4.y); hit(v4.z); hit(v4.w);
                 }
-                if (rc_lo) atomicAdd(hist + wl.off + rb_lo, (unsigned long long)rc_lo);
-                if (rc_hi) atomicAdd(hist + wh.off + rb_hi, (unsigned long long)rc_hi);
                 atomicAdd(a.acc + ACC_HDR + grow, (unsigned long long)sum);
                 if (clo) atomicAdd(a.acc + ACC_HDR + R + 2 * grow, (unsigned long long)clo);
                 if (chi) atomicAdd(a.acc + ACC_HDR + R + 2 * grow + 1, (unsigned long long)chi);
@@ -625,7 +683,7 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
 __global__ void __launch_bounds__(256) vx_fold_matrix_kernel(const int32_t *__restrict__ dump,
                                                              int64_t ld, int64_t c0, int64_t c1,
                                                              const Win *__restrict__ wins,
-                                                             unsigned long long *acc, int R)
+                                                             unsigned long long *acc, int R, int bins64)
 {
     __shared__ unsigned long long sh[3][256];
     const int row = blockIdx.x;
@@ -638,8 +696,8 @@ __global__ void __launch_bounds__(256) vx_fold_matrix_kernel(const int32_t *__re
         sum += (unsigned long long)(uint32_t)v;
         const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
         clo += dl >> 31; chi += dh >> 31;
-        if (dl < wl.len) atomicAdd(hist + wl.off + (dl >> wl.shift), 1ull);
-        if (dh < wh.len) atomicAdd(hist + wh.off + (dh >> wh.shift), 1ull);
+        if (dl < wl.len) bin_add(hist, wl.off + (dl >> wl.shift), bins64);
+        if (dh < wh.len) bin_add(hist, wh.off + (dh >> wh.shift), bins64);
     }
     sh[0][threadIdx.x] = sum; sh[1][threadIdx.x] = clo; sh[2][threadIdx.x] = chi;
     __syncthreads();
@@ -915,13 +973,16 @@ __global__ void __launch_bounds__(256) vx_extract_kernel(const unsigned long lon
                                                          const Win *__restrict__ wins,
                                                          const int *__restrict__ kind,
                                                          long long *__restrict__ res, int R,
-                                                         double q_lo, double q_hi)
+                                                         double q_lo, double q_hi, int bins64)
 {
     const int gw = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (gw >= 2 * R) return;
     const Win w = wins[gw];
     const uint32_t nb = w.len >> w.shift;
-    const unsigned long long *hist = acc + ACC_HDR + 3 * (int64_t)R + w.off;
+    const unsigned long long *hist64 = acc + ACC_HDR + 3 * (int64_t)R;
+    const unsigned int *hist32 = reinterpret_cast<const unsigned int *>(hist64) + w.off;
+    hist64 += w.off;
+    auto bin = [&](uint32_t b) -> long long { return bins64 ? (long long)hist64[b] : (long long)hist32[b]; };
     const long long below = (long long)acc[ACC_HDR + R + gw];
     long long rk[4];
     quantile_ranks((long long)acc[0], q_lo, rk[0], rk[1]);
@@ -935,10 +996,10 @@ __global__ void __launch_bounds__(256) vx_extract_kernel(const unsigned long lon
     long long cum = below;
     for (uint32_t b0 = 0; b0 < nb && (t[0] >= 0 || t[1] >= 0); b0 += 128) {
         const uint32_t b = b0 + 4 * lane;                    // 4 bins per lane: 4 loads in flight
-        const long long h0 = (b < nb) ? (long long)hist[b] : 0;
-        const long long h1 = (b + 1 < nb) ? (long long)hist[b + 1] : 0;
-        const long long h2 = (b + 2 < nb) ? (long long)hist[b + 2] : 0;
-        const long long h3 = (b + 3 < nb) ? (long long)hist[b + 3] : 0;
+        const long long h0 = (b < nb) ? bin(b) : 0;
+        const long long h1 = (b + 1 < nb) ? bin(b + 1) : 0;
+        const long long h2 = (b + 2 < nb) ? bin(b + 2) : 0;
+        const long long h3 = (b + 3 < nb) ? bin(b + 3) : 0;
         const long long lsum = h0 + h1 + h2 + h3;
         long long incl = lsum;                                // inclusive warp scan
         for (int o = 1; o < 32; o <<= 1) {
@@ -983,12 +1044,12 @@ __global__ void vx_test_poisson_kernel(float lam, int64_t n, uint64_t seed, int3
     normal_pair(r.x, r.y, z1, z2);
     if (exact) {
         const PhiloxKeys K = philox_keys(seed);
-        out[i] = poisson_draw_exact(lam, r.z, (uint32_t)i, (uint32_t)(i >> 32), 3u, 0u, K);
+        out[i] = poisson_draw_exact(lam, (uint32_t)i, (uint32_t)(i >> 32), 3u, 0u, K);
         return;
     }
     // the stepper's own code path: packed coefficients for the pair, first / second draw by parity
     const CFCoef cf = cf_coefficients(z1, z2);
-    out[i] = (i & 1) ? poisson_draw_c<1>(lam, z2, cf, r.w) : poisson_draw_c<0>(lam, z1, cf, r.z);
+    out[i] = (i & 1) ? poisson_draw_c<1>(lam, z2, cf) : poisson_draw_c<0>(lam, z1, cf);
 }
 
 __global__ void vx_test_normal_kernel(int64_t n, uint64_t seed, float *out)
