@@ -324,7 +324,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    all_reduce, all_reduce_async = dmod.make_torch_reducers(dist, local_rank) if dist else (None, None)
+    all_reduce = dmod.make_torch_reducer(dist) if dist else None
 
     def one_job(seed):
         cfg = nat.make_config(bounds, N_POP, T_DAYS, n_global, seed, q_lo, q_hi,
@@ -332,7 +332,7 @@ def main():
         if world == 1:
             return ctx.run_bounds(cfg)
         return dmod.run_sharded(dmod.ContextEngine(ctx), cfg, rank, world, all_reduce,
-                                lambda: nat.ResultBuffers(T_DAYS), all_reduce_async)
+                                lambda: nat.ResultBuffers(T_DAYS))
 
     # ---------------- device-timed leg ("value")
     for i in range(args.warmup):

@@ -10,9 +10,11 @@ The directory name contains hyphens, so import it with importlib (or through the
                                       dict(start_date="2020-12-15", end_date="2022-07-1"))
 
 Contents: csrc/ (CUDA kernels + C ABI, built in-tree to libvaxmc.so), _native (ctypes),
-model (the reference's run_model / CLI interface), distributed (sample sharding + NCCL merge).
+model (the reference's run_model / CLI interface), distributed (sample sharding + NCCL merge),
+country_data (offline-safe get_country_data for the app's overlay).
 """
-from . import _native, build, distributed, model  # noqa: F401
+from . import _native, build, country_data, distributed, model  # noqa: F401
+from .country_data import get_country_data  # noqa: F401
 from ._native import Context, VaxmcError, default_context  # noqa: F401
 from .model import (  # noqa: F401
     SERIES, cache_clear, main, results_to_jsonable, run_model, run_model_grid, run_model_quantiles, run_sampling,
@@ -22,5 +24,5 @@ from .model import (  # noqa: F401
 __all__ = [
     "run_model", "run_model_grid", "run_model_quantiles", "run_sampling", "sample_param_combinations", "run_single_realization", "seed",
     "main", "SERIES", "Context", "VaxmcError", "default_context", "cache_clear",
-    "results_to_jsonable",
+    "results_to_jsonable", "get_country_data",
 ]

@@ -2,13 +2,11 @@
 
 The path shards by independent units: every sample is independent
 (model.py:176-179) and its Philox stream is keyed by its GLOBAL id, so rank r simply folds
-the contiguous range shard_range(n, r, world).  The only exchange steps are
-
-  1. one all-reduce(sum) of four float64 (rejection count and the moments of p_soft_no,
-     model.py:280-287, 339-342), and
-  2. per streaming pass, one all-reduce(sum) of the int64 accumulator slab (per-date sums,
-     counts below the windows, window histograms) -- integer addition, hence results that
-     are bit-identical for 1/2/4/8 GPUs.
+the contiguous range shard_range(n, r, world).  The only exchange step is, per streaming
+pass, ONE all-reduce(sum) of the int64 accumulator slab (per-date sums, counts below the
+windows, window histograms; the shard's rejection count and the fixed-point moments of
+p_soft_no, model.py:280-287, 339-342, ride in its header) -- integer addition, hence results
+that are bit-identical for 1/2/4/8 GPUs.
 
 torch.distributed is plumbing only (process group + the NCCL call on a tensor that aliases
 the library's device slab); all arithmetic is in libvaxmc.so.
@@ -84,13 +82,22 @@ class ContextEngine:
         return torch.from_numpy(st).to(f"cuda:{self.ctx.device}")
 
 
-def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out, all_reduce_async=None):
+def bounds_infeasible(cfg) -> bool:
+    """No acceptable (p_pro, p_anti) pair exists in the box: the reference burns 10*n_rep + 1
+    rejections and returns (None, None) (model.py:280-287).  A property of cfg alone, so every
+    rank takes the same decision without talking to the others."""
+    b = cfg.bounds
+    return min(b[0], b[1]) + min(b[2], b[3]) > 1.0
+
+
+def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out):
     """Drive one rank of a sharded job.  `all_reduce(tensor)` sums in place across ranks and
     returns when the result is usable.
 
     One collective per pass: the shard's parameter statistics (rejections, moments of
-    p_soft_no) ride in the header of the int64 slab.  A direct job (n <= direct_max) is computed
-    whole on every rank and needs no collective at all.
+    p_soft_no) ride in the header of the int64 slab, and the 10*n_rep abort rule is decided on
+    the MERGED count (a rank must never leave before a collective the others still enter).  A
+    direct job (n <= direct_max) is computed whole on every rank and needs no collective at all.
     """
     direct = cfg.n_samples <= (cfg.direct_max if cfg.direct_max > 0 else nat.DIRECT_MAX_DEFAULT) \
         or cfg.mode == nat.MODE_EXPECTED
@@ -102,8 +109,8 @@ def run_sharded(engine, cfg, rank: int, world: int, all_reduce, make_out, all_re
         st = engine.param_stats()
         trace("param_stats")
         out = make_out()
-        if st[0] > 10.0 * cfg.n_samples:          # this shard alone already breaks the 10*n_rep rule
-            out.c.aborted = 1
+        if getattr(cfg, "bounds", None) is not None and bounds_infeasible(cfg):
+            out.c.aborted = 1                     # certain on every rank: nobody enters a collective
             out.c.n_rejected = int(st[0])
             return out
         engine.pilot()
@@ -144,8 +151,8 @@ class _Trace:
             self.t = now
 
 
-def make_torch_reducers(dist, device):
-    """(all_reduce, all_reduce_async) over torch.distributed for tensors on `device`.
+def make_torch_reducer(dist):
+    """all_reduce(tensor) over torch.distributed.
 
     The library synchronises its own stream before returning from every staged call, so the
     collective only has to be complete before the next library call."""
@@ -156,16 +163,22 @@ def make_torch_reducers(dist, device):
         if t.is_cuda:
             torch.cuda.current_stream(t.device).synchronize()
 
-    def all_reduce_async(t):
-        work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+    return all_reduce
 
-        def wait():
-            work.wait()
-            if t.is_cuda:
-                torch.cuda.current_stream(t.device).synchronize()
-        return wait
 
-    return all_reduce, all_reduce_async
+def broadcast_seed(key: int) -> int:
+    """Rank 0's Philox key on every rank.  An entropy seed (seed=None, the reference's default
+    call) is drawn independently per process; the replicated pilot and the window plan must
+    come from ONE key or the ranks would all-reduce slabs of different shapes."""
+    try:
+        import torch.distributed as dist
+    except ImportError:
+        return key
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return key
+    box = [int(key)]
+    dist.broadcast_object_list(box, src=0)
+    return int(box[0])
 
 
 def run_job(cfg, device=None):
@@ -185,6 +198,5 @@ def run_job(cfg, device=None):
     ctx = nat.default_context(int(device))
     if world == 1:
         return ctx.run_bounds(cfg)
-    all_reduce, all_reduce_async = make_torch_reducers(dist, ctx.device)
-    return run_sharded(ContextEngine(ctx), cfg, dist.get_rank(), world, all_reduce,
-                       lambda: nat.ResultBuffers(cfg.T), all_reduce_async)
+    return run_sharded(ContextEngine(ctx), cfg, dist.get_rank(), world, make_torch_reducer(dist),
+                       lambda: nat.ResultBuffers(cfg.T))

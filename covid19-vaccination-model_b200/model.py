@@ -49,13 +49,20 @@ def seed(value: int | None):
     _seed_state["calls"] = 0
 
 
-def _next_seed(explicit: int | None) -> tuple[int, bool]:
-    """(Philox key, deterministic?) for the next job."""
+def _next_seed(explicit: int | None, collective: bool = False) -> tuple[int, bool]:
+    """(Philox key, deterministic?) for the next job.  `collective`: the caller is an entry point
+    that every rank of a torchrun job enters (run_model, run_model_quantiles); an entropy key is
+    then rank 0's on every rank (distributed.broadcast_seed) -- one job has one key."""
     if explicit is not None:
         return int(explicit) & 0xFFFFFFFFFFFFFFFF, True
     base = _seed_state["base"]
     if base is None:
-        return int.from_bytes(os.urandom(8), "little"), False
+        key = int.from_bytes(os.urandom(8), "little")
+        if collective:
+            from . import distributed as dist_
+
+            key = dist_.broadcast_seed(key)
+        return key, False
     k = _seed_state["calls"]
     _seed_state["calls"] = k + 1
     # first job after seed(v) uses v itself; later jobs a fixed odd-multiplier walk from it
@@ -151,7 +158,7 @@ def run_model(
     ci_frac = CI / 100
     daily, weekly = _dates(date_range["start_date"], date_range["end_date"])
     T = len(daily)
-    key_seed, deterministic = _next_seed(seed)
+    key_seed, deterministic = _next_seed(seed, collective=True)
     vx_mode = nat.MODE_EXPECTED if mode == "expected" else nat.MODE_STOCHASTIC
 
     cache_key = None
@@ -259,7 +266,7 @@ def run_model_quantiles(p_pro_bounds, p_anti_bounds, pressure_bounds, tau_bounds
     qs = sorted(float(q) for q in quantiles)
     if not qs or qs[0] < 0.0 or qs[-1] > 1.0:
         raise ValueError("quantiles must be fractions in [0, 1]")
-    key_seed, _ = _next_seed(seed)
+    key_seed, _ = _next_seed(seed, collective=True)
     bounds = _bounds12(np.array(p_pro_bounds) / 100, np.array(p_anti_bounds) / 100,
                        np.array(pressure_bounds), np.array(tau_bounds), np.array(nv_0_bounds) / 100,
                        np.array(nv_max_bounds) / 100)

@@ -135,5 +135,40 @@ def main():
         print(f"  {f}  {os.path.getsize(os.path.join(OUT, f))} B")
 
 
+def country_data_golden():
+    """N4: the reference's own get_country_data (plot.py:8-36) on the committed fixture CSV.
+    plot.py imports plotly (absent here) -> stub modules; pd.read_csv is pointed at the fixture
+    instead of the OWID URL.  Output: tests/golden/country_data_pivot.csv."""
+    import sys
+    import types
+
+    import pandas as pd
+
+    for name in ("plotly", "plotly.express", "plotly.graph_objects", "plotly.subplots"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["plotly.express"].colors = types.SimpleNamespace(qualitative=types.SimpleNamespace(Safe=["#000"] * 12))
+    sys.modules["plotly.subplots"].make_subplots = lambda *a, **k: None
+    sys.modules.pop("plot", None)                      # the harness' stub `plot` must not shadow the real one
+    sys.path.insert(0, "/root/reference")
+    import plot as ref_plot
+
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden",
+                           "owid_vaccinations_sample.csv")
+    real = pd.read_csv
+    pd.read_csv = lambda *a, **k: real(fixture)
+    try:
+        countries, pivot = ref_plot.get_country_data()
+    finally:
+        pd.read_csv = real
+    pivot.to_csv(os.path.join(os.path.dirname(fixture), "country_data_pivot.csv"))
+    with open(os.path.join(os.path.dirname(fixture), "country_data_countries.txt"), "w") as f:
+        f.write("\n".join(countries) + "\n")
+    print("country data golden:", pivot.shape, list(countries))
+
+
 if __name__ == "__main__":
-    main()
+    if "--country-data" in sys.argv:       # only the N4 fixture (does not touch the model goldens)
+        country_data_golden()
+    else:
+        main()
+        country_data_golden()

@@ -40,8 +40,9 @@ class FakeEngine:
     """Integer fold of f(id) = (id * 2654435761) % 1009 over the shard, two passes; the shard's
     rejection count rides in word 2 of the slab, as in libvaxmc."""
 
-    def __init__(self, infeasible=False):
+    def __init__(self, infeasible=False, skewed_rank=None):
         self.infeasible = infeasible
+        self.skewed_rank = skewed_rank      # this rank ALONE exceeds 10*n rejections, the others see none
         self.passes = 0
         self.calls = []
 
@@ -52,6 +53,8 @@ class FakeEngine:
     def param_stats(self):
         ids = np.arange(self.first, self.first + self.count, dtype=np.int64)
         self.rej = int((ids % 3 == 0).sum()) if not self.infeasible else 11 * self.count
+        if self.skewed_rank is not None:
+            self.rej = 10 * self.n + 5 if dist.get_rank() == self.skewed_rank else 0
         s = (ids % 100) / 100.0
         return np.array([float(self.rej), s.sum(), (s * s).sum(), float(self.count)])
 
@@ -104,7 +107,40 @@ def _worker(rank, world, port, n, q):
         out = d.run_sharded(eng, _Cfg(n), rank, world, all_reduce, _Out)
         bad = FakeEngine(infeasible=True)
         out_bad = d.run_sharded(bad, _Cfg(n), rank, world, all_reduce, _Out)
-        q.put((rank, out.merged.tolist(), eng.passes, n_reduces[0], eng.calls, out_bad.c.aborted, bad.passes))
+        # one shard alone breaks the 10*n rule, the other sees no rejection at all: both ranks must
+        # still meet in the collective and BOTH report the abort (no early return, no hang)
+        skew = FakeEngine(skewed_rank=0)
+        out_skew = d.run_sharded(skew, _Cfg(n), rank, world, all_reduce, _Out)
+        # entropy seeds differ per process; a collective entry point must end up with rank 0's
+        key = d.broadcast_seed(1000 + rank)
+        m = importlib.import_module(PKG + ".model")
+        m.seed(None)
+        k2, det = m._next_seed(None, collective=True)
+        k3, _ = m._next_seed(None)                      # non-collective: stays local
+        keys = [torch.tensor([k2 >> 32, k2 & 0xFFFFFFFF, k3 >> 32, k3 & 0xFFFFFFFF], dtype=torch.int64)
+                for _ in range(world)]
+        dist.all_gather(keys, keys[rank].clone())
+        # result cache under torchrun: every rank must take the same hit/miss decision,
+        # or one would sit in the job's all-reduce alone.  The stand-in job does a real collective.
+        jobs = []
+
+        def fake_job(cfg, device=None):
+            t = torch.tensor([int(cfg.seed & 0x7FFFFFFF)], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            jobs.append((int(t.item()), int(cfg.seed & 0x7FFFFFFF)))
+            ob = m.nat.ResultBuffers(cfg.T)
+            ob.c.n_finished = cfg.n_samples
+            return ob
+
+        d.run_job = fake_job
+        m.cache_clear()
+        a = ([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95, 100, 50000,
+             dict(start_date="2021-01-01", end_date="2021-01-10"))
+        m.run_model(*a, seed=5); m.run_model(*a, seed=5)          # miss, hit
+        m.run_model(*a); m.run_model(*a)                          # entropy seed: two jobs, one key each
+        m.run_model(*a, seed=5)                                   # still a hit
+        q.put((rank, out.merged.tolist(), eng.passes, n_reduces[0], eng.calls, out_bad.c.aborted, bad.passes,
+               out_skew.c.aborted, skew.passes, key, det, [k.tolist() for k in keys], jobs))
     finally:
         dist.destroy_process_group()
 
@@ -139,10 +175,14 @@ def test_two_rank_gloo_merge_equals_single_rank(n):
         p.join(timeout=60)
         assert p.exitcode == 0
     merged = _expected(n)
-    for rank, m, passes, n_red, calls, aborted, bad_passes in res:
+    for rank, m, passes, n_red, calls, aborted, bad_passes, skew_aborted, skew_passes, key, det, keys, jobs in res:
+        assert len(jobs) == 3 and all(mx == own for mx, own in jobs)     # same hit/miss and same key on every rank
         assert np.array_equal(np.array(m), merged)              # integer merge is exact
         assert passes == 2                                       # one VX_REFINE round trip
-        assert n_red == 2 + 1                                    # ONE collective per pass (+1: the aborting job)
+        assert n_red == 2 + 1 + 1                                # ONE collective per pass (+1 +1: the two aborting jobs)
+        assert skew_aborted == 1 and skew_passes == 1            # decided on the MERGED count, on every rank
+        assert key == 1000 and not det                           # rank 0's key everywhere
+        assert keys[0][:2] == keys[1][:2] and keys[0][2:] != keys[1][2:]
         assert calls[0][0] == "begin" and calls[1] == ("pilot",) and calls[-1] == ("end",)
         # neither shard alone breaks the 10*n rule (11*n/2 each); the merged count does
         assert aborted == 1 and bad_passes == 1
