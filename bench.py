@@ -34,6 +34,7 @@ for _p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, _p)
 
 PKG = "covid19-vaccination-model_b200"
+PKG_DIR = PKG
 USA = dict(pro=[35, 45], anti=[12, 25], pressure=[0.0, 0.02], tau=[5, 7], nv0=[1, 1.2], nvmax=[5, 10])
 DATES = dict(start_date="2020-12-15", end_date="2022-07-1")
 T_DAYS = 564
@@ -45,10 +46,14 @@ WIDE_DATES = dict(start_date="2020-12-15", end_date="2025-12-14")
 WIDE_T = 1826
 BYTES_PER_SAMPLE_WEEK = 112.0   # 4 int32 counts per sample-day if materialised
 HBM_FALLBACK_GBS = 6650.0       # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-# from profiles/r01_fold_vi_ncu_summary.txt (ncu --set full of this kernel, this workload, 1e6 samples)
-NCU_WARP_INST_PER_WARP_DAY = 198.5   # smsp__inst_executed.sum / (samples*days/32)
-NCU_DRAM_BYTES_PER_LAUNCH = 3.46e7   # dram__bytes_read.sum + dram__bytes_write.sum
 N_SM, SCHEDULERS_PER_SM = 148, 4
+# ncu counters of the dominant kernel (instructions and DRAM bytes per launch) live in a committed
+# file keyed by the sha256 of the kernel source they were captured from: a kernel edit without a
+# new capture makes the roofline fraction null ("stale_counters") instead of silently wrong.
+COUNTERS_JSON = os.path.join(ROOT, "profiles", "kernel_counters.json")
+KERNEL_SOURCE = os.path.join(ROOT, PKG_DIR, "csrc", "vaxmc_kernels.cuh")
+# north_star check (3) on the driver's path: one FIXED global job whose digest must not depend on N
+BITEXACT_JOB = dict(samples=3_000_000, seed=12345, ci=95)
 
 
 def bounds_frac(b):
@@ -143,50 +148,102 @@ def measured_hbm_peak():
         return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
 
 
-def cpu_port_rate(n_samples: int, threads: int, seed: int = 1):
+def load_counters():
+    """profiles/kernel_counters.json if it was captured from the kernel source that is built now."""
+    import hashlib
+
+    try:
+        with open(KERNEL_SOURCE, "rb") as f:
+            sha = hashlib.sha256(f.read()).hexdigest()
+    except OSError:
+        return None, {"stale_counters": True, "why": "kernel source not found"}
+    try:
+        with open(COUNTERS_JSON) as f:
+            c = json.load(f)
+    except Exception:
+        return None, {"stale_counters": True, "why": "profiles/kernel_counters.json missing", "kernels_sha256": sha}
+    if c.get("kernels_sha256") != sha:
+        return None, {"stale_counters": True, "kernels_sha256": sha, "counters_sha256": c.get("kernels_sha256"),
+                      "why": "vaxmc_kernels.cuh changed since the ncu capture behind profiles/kernel_counters.json"}
+    return c, {"stale_counters": False, "kernels_sha256": sha, "source": c.get("source")}
+
+
+def workload_config(args, world):
+    """The `config` block: identical for the native arm and the reference arm of one run."""
+    wide = args.workload == "wide5y"
+    return {"workload": ("wide-uncertainty 5-year sweep at %g samples per GPU (BASELINE configs[3]); " if wide else
+                         "README USA scenario at %g samples per GPU (BASELINE configs[1]); ") % args.samples
+                        + "global range = n_gpus x samples_per_gpu, sharded by sample id",
+            "samples_per_gpu": args.samples, "samples_global": args.samples * world,
+            "days": WIDE_T if wide else T_DAYS, "N": N_POP, "CI": args.ci if args.ci is not None else CI_PCT,
+            "seed": "2000+step", "l2": "flushed between steps (256 MiB memset)"}
+
+
+def cpu_port_rate(n_samples: int, threads: int, seed: int = 1, bounds=None, T=None):
     """sample-weeks/s of the oracle port (C restatement of model.py:29-136 with numpy's own
     MT19937 + Poisson algorithms) on `threads` host threads, incl. the per-date reduction."""
     import numpy as np
 
     import ref_oracle as ro
 
+    T = T or T_DAYS
     mt = ro.MT(seed)
-    b = usa_bounds_frac()
+    b = usa_bounds_frac() if bounds is None else bounds
     params, _ = ro.sample_param_combinations(mt, b[0:2], b[2:4], b[4:6], b[6:8], b[8:10], b[10:12],
                                              n_samples)
-    ro.bulk_counts(seed, params[:256], T_DAYS, N_POP, threads=threads)      # warm caches / build
+    ro.bulk_counts(seed, params[:256], T, N_POP, threads=threads)      # warm caches / build
     t0 = time.perf_counter()
-    daily, weekly = ro.bulk_counts(seed, params, T_DAYS, N_POP, threads=threads)
+    daily, weekly = ro.bulk_counts(seed, params, T, N_POP, threads=threads)
     for arr in (daily[0], daily[1], daily[2], weekly):                      # model.py:220-223
         np.quantile(arr, [0.025, 0.975], axis=1)
         arr.mean(axis=1)
     dt = time.perf_counter() - t0
-    return n_samples * T_DAYS / 7.0 / dt, dt
+    return n_samples * T / 7.0 / dt, dt
 
 
 def run_reference_arm(args):
+    """The reference's CPU algorithm for this path on the box's host cores (the C port: the
+    reference itself is pure Python and cannot travel to the GPU box).  Same `config` as the
+    native arm; each step is a bounded sample of that workload (--cpu-samples), and the line
+    states how the rate behaves between that sample and the full per-GPU size (`linearity`) and
+    what ONE core does (`single_thread`), as BASELINE.md section 3 asks."""
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
+    wide = args.workload == "wide5y"
+    bounds, T = (bounds_frac(WIDE), WIDE_T) if wide else (usa_bounds_frac(), T_DAYS)
     threads = os.cpu_count() or 1
     n = args.cpu_samples
     rates, times = [], []
     for i in range(args.warmup + args.steps):
-        r, dt = cpu_port_rate(n, threads, seed=100 + i)
+        r, dt = cpu_port_rate(n, threads, seed=100 + i, bounds=bounds, T=T)
         if i >= args.warmup:
             rates.append(r); times.append(dt)
-    value = n * T_DAYS / 7.0 * len(times) / sum(times)
-    sample = (f"{n} samples x {T_DAYS} days per step (USA scenario), C port of model.py with "
-              f"numpy-identical MT19937/Poisson, {threads} pthreads, np.quantile+mean per date")
+    value = n * T / 7.0 * len(times) / sum(times)
+    # the same port once at the native arm's full per-GPU size, and on one thread
+    full_rate, full_dt = cpu_port_rate(args.samples, threads, seed=7, bounds=bounds, T=T) \
+        if args.samples * T <= 1.2e9 else (None, None)
+    one_rate, one_dt = cpu_port_rate(max(n // 10, 1000), 1, seed=8, bounds=bounds, T=T)
+    sample = (f"{n} samples x {T} days per step, C port of model.py with numpy-identical MT19937/Poisson, "
+              f"{threads} pthreads, np.quantile+mean per date")
     line = {
         "impl": "reference", "metric": "MC sample-weeks/sec", "value": value, "unit": "sample-weeks/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64/f64", "data": "synthetic",
-        "config": {"workload": "README USA scenario (configs[1] bounds), bounded CPU sample",
-                   "samples_per_step": n, "days": T_DAYS, "N": N_POP, "CI": CI_PCT},
+        "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "sample-weeks/s", "cores": threads, "kind": "port",
                          "sample": sample},
+        "linearity": {"samples": [n, args.samples], "rate": [value, full_rate],
+                      "ratio_full_over_sample": (full_rate / value) if full_rate else None,
+                      "full_size_s": full_dt,
+                      "note": "CPU rate at the bounded per-step sample vs ONE pass at the native arm's full "
+                              "per-GPU size: the rate is flat in n, so the bounded sample stands for the config"},
+        "single_thread": {"value": one_rate, "unit": "sample-weeks/s", "cores": 1, "samples": max(n // 10, 1000),
+                          "seconds": one_dt,
+                          "note": "per-core figure (BASELINE.md 3); the reference's own pure-Python loop "
+                                  "measured 3.5-4.0e4 sample-weeks/s per core in the survey container"},
         "e2e": {"value": value, "unit": "sample-weeks/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -273,6 +330,8 @@ def main():
     ap.add_argument("--ci", type=float, default=None, help="CI in percent (default 95; grid: 99)")
     ap.add_argument("--direct", action="store_true",
                     help="force the materialise + radix-select path (HBM-bound passes) instead of the streaming fold")
+    ap.add_argument("--target-samples", type=int, default=1_000_000_000,
+                    help="global samples of the target_1e9 block (BASELINE configs[2]); 0 skips it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -391,47 +450,108 @@ def main():
                "ms_per_step": 1e3 * float(tt.item()) / len(e2e_s),
                "api": "run_model(...) of covid19-vaccination-model_b200 (ctypes -> C ABI)"}
 
+    # ---------------- north_star check (3): ONE fixed global job, whatever N is.  Its digest must be
+    # the same on every line of a 1/2/4/8-GPU scaling run (integer slab merge => bit-identical).
+    import hashlib
+
+    bj = BITEXACT_JOB
+    res, err, msg = vax.run_model(USA["pro"], USA["anti"], USA["pressure"], USA["tau"], USA["nv0"], USA["nvmax"],
+                                  bj["ci"], bj["samples"], N_POP, DATES, seed=bj["seed"])
+    h = hashlib.sha256()
+    for k in vax.SERIES:
+        for f in ("mean", "lower", "upper"):
+            h.update(np.ascontiguousarray(res[k][f], dtype=np.float64).tobytes())
+    digest = h.hexdigest()
+    dg = torch.tensor([int(digest[:15], 16)], dtype=torch.int64, device=f"cuda:{local_rank}")
+    lo, hi = dg.clone(), dg.clone()
+    if dist is not None:
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    bitexact = {"job": "USA scenario, n=%d, seed=%d, CI=%g, sharded over n_gpus ranks" % (bj["samples"], bj["seed"], bj["ci"]),
+                "n": bj["samples"], "sha256": digest, "arrays": "mean,lower,upper of the 4 series (float64 bytes)",
+                "identical_on_all_ranks": bool(lo.item() == hi.item()), "agnostics": msg, "error": err}
+
+    # ---------------- BASELINE configs[2] / second half of `metric`: wall time to CI bands at 1e9
+    # samples (global, over the N ranks), through run_model
+    target = None
+    if args.target_samples > 0 and args.workload == "usa":
+        tw = []
+        for i in range(1 + 3):
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r9, e9, _ = vax.run_model(USA["pro"], USA["anti"], USA["pressure"], USA["tau"], USA["nv0"], USA["nvmax"],
+                                      95, args.target_samples, N_POP, DATES, seed=9000 + i)
+            chk = float(r9["people_vaccinated_per_hundred"]["upper"][-1])
+            dt = time.perf_counter() - t0
+            assert e9 == "" and chk > 0 and r9["number_finished_samples"] == args.target_samples
+            if i >= 1:
+                tw.append(dt)
+        tt9 = torch.tensor([sum(tw)], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if dist is not None:
+            dist.all_reduce(tt9, op=dist.ReduceOp.MAX)
+        wall = float(tt9.item()) / len(tw)
+        target = {"workload": "README USA scenario, %g samples GLOBAL over %d GPU(s), CI=95 (BASELINE configs[2])"
+                              % (args.target_samples, world),
+                  "samples_global": args.target_samples, "wall_s_to_ci_bands": wall,
+                  "sample_weeks_per_s": args.target_samples * 564 / 7.0 / wall, "timed_calls": len(tw),
+                  "warmup_calls": 1, "api": "run_model(..., n_rep=%d, CI=95), host wall clock, max over ranks"
+                                            % args.target_samples}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
     # ---------------- roofline of the dominant kernel (the streaming-fold stepper)
-    peak, peak_src = measured_hbm_peak()
+    # The stepper reads and writes (almost) nothing: it is bound by instruction issue, so the
+    # fraction is warp instructions issued per second over what 148 SMs x 4 schedulers can issue
+    # at the SM clock sampled during this run.  Instructions per launch come from the committed ncu
+    # capture of THIS kernel source (profiles/kernel_counters.json), the duration from this run's
+    # CUDA events.
+    peak_hbm, peak_src = measured_hbm_peak()
     fold_ms_avg = sum(fold_ms) / max(fold_launches, 1)       # per launch, rank 0, CUDA events
-    units_per_launch = args.samples * T_DAYS / 7.0 * (sum(passes) / max(fold_launches, 1) if fold_launches else 1)
-    units_per_launch = args.samples * T_DAYS / 7.0
-    achieved = BYTES_PER_SAMPLE_WEEK * units_per_launch / (fold_ms_avg * 1e-3) / 1e9 if fold_launches else None
-    roofline = {
-        "kernel": "vx_sim_kernel<SIM_FOLD>", "bound": "hbm",
-        "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": (achieved / peak) if achieved else None,
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH * (args.samples / 1e6) if args.workload == "usa" else None,
-        "peak_source": peak_src,
-        "ms_per_launch": fold_ms_avg, "share_of_step": sum(fold_ms) / sum(dev_ms) if sum(dev_ms) else None,
-        "note": ("algorithmic bytes = 112 B per sample-week (the int32 trajectories of SURVEY.md 8d) x "
-                 "sample-weeks per launch; the kernel folds them on the fly instead of writing them, so "
-                 "its real bound is instruction issue (see issue_roofline and DESIGN.md), and dram traffic "
-                 "is ~0 by design"),
-    }
-    sd_per_s = args.samples * T_DAYS / (fold_ms_avg * 1e-3) if fold_launches else None
+    counters, cstate = load_counters()
     sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
-    issue_peak = N_SM * SCHEDULERS_PER_SM * sm_hz                      # warp-instructions/s the SMs can issue
-    issue_ach = NCU_WARP_INST_PER_WARP_DAY * (sd_per_s / 32.0) if sd_per_s else None
-    issue = {"bound": "issue", "sample_days_per_s_per_gpu": sd_per_s,
-             "warp_inst_per_warp_day": NCU_WARP_INST_PER_WARP_DAY,
-             "achieved": issue_ach, "peak": issue_peak, "unit": "warp-inst/s",
-             "frac": (issue_ach / issue_peak) if issue_ach else None,
-             "note": "the stepper's real roofline: warp instructions issued per second (instruction count per "
-                     "warp-day from the ncu capture in profiles/, rate from this run's CUDA events) over "
-                     "148 SMs x 4 schedulers x the SM clock sampled during the run"}
+    issue_peak = N_SM * SCHEDULERS_PER_SM * sm_hz
+    sample_days = args.samples * T_DAYS
+    sd_per_s = sample_days / (fold_ms_avg * 1e-3) if fold_launches else None
+    inst_per_launch = traffic = issue_ach = None
+    if counters is not None and fold_launches and args.workload == "usa":
+        scale = sample_days / float(counters["sample_days_per_launch"])
+        inst_per_launch = counters["warp_inst_per_launch"] * scale
+        traffic = counters["dram_bytes_per_launch"] * scale
+        issue_ach = inst_per_launch / (fold_ms_avg * 1e-3)
+    hbm_equiv = BYTES_PER_SAMPLE_WEEK * (sample_days / 7.0) / (fold_ms_avg * 1e-3) / 1e9 if fold_launches else None
+    roofline = {
+        "kernel": "vx_sim_kernel<SIM_FOLD>", "bound": "issue",
+        "achieved": issue_ach, "peak": issue_peak, "unit": "warp-inst/s",
+        "frac": (issue_ach / issue_peak) if issue_ach else None,
+        "traffic": traffic,
+        "peak_source": "148 SMs x 4 warp schedulers x SM clock sampled during the timed region (%.0f MHz)" % (sm_hz / 1e6),
+        "ms_per_launch": fold_ms_avg, "share_of_step": sum(fold_ms) / sum(dev_ms) if sum(dev_ms) else None,
+        "warp_inst_per_launch": inst_per_launch,
+        "warp_inst_per_warp_day": (inst_per_launch / (sample_days / 32.0)) if inst_per_launch else None,
+        "sample_days_per_s_per_gpu": sd_per_s,
+        "counters": cstate,
+        "hbm_equivalent": {"bound": "hbm", "achieved": hbm_equiv, "peak": peak_hbm, "unit": "GB/s",
+                           "frac": (hbm_equiv / peak_hbm) if hbm_equiv else None, "peak_source": peak_src,
+                           "note": "SURVEY 8(d)'s 112 B per sample-week (the int32 trajectories IF materialised) over "
+                                   "the kernel time; the kernel folds them on the fly, so these bytes never move "
+                                   "(see traffic): a derived figure, not the bound"},
+        "note": "issue-bound stepper (Philox + sampler arithmetic in registers, DRAM traffic ~0 by design): "
+                "achieved = ncu smsp__inst_executed.sum per launch (profiles/kernel_counters.json, same kernel "
+                "source by sha256) / CUDA-event launch time of this run",
+    }
+    if cstate.get("stale_counters"):
+        roofline["stale_counters"] = True
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        rate, dt = cpu_port_rate(args.cpu_samples, threads)
+        rate, dt = cpu_port_rate(args.cpu_samples, threads, bounds=bounds, T=T_DAYS)
         cpu = {"value": rate, "unit": "sample-weeks/s", "cores": threads, "kind": "port",
-               "sample": f"{args.cpu_samples} samples x {T_DAYS} days of the same USA workload "
+               "sample": f"{args.cpu_samples} samples x {T_DAYS} days of the same workload "
                          f"({dt:.1f} s), C port of model.py, {threads} pthreads"}
 
     line = {
@@ -439,18 +559,15 @@ def main():
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32 state / fp32 sampler / fp64 arrivals", "data": "synthetic",
-        "config": {"workload": ("README USA scenario at %g samples per GPU (BASELINE configs[1]); " % args.samples
-                                if args.workload == "usa" else
-                                "wide-uncertainty 5-year sweep at %g samples per GPU (BASELINE configs[3]); " % args.samples)
-                               + "global range = n_gpus x samples_per_gpu, sharded by sample id",
-                   "samples_per_gpu": args.samples, "samples_global": n_global, "days": T_DAYS,
-                   "N": N_POP, "CI": CI_PCT, "seed": "2000+step", "l2": "flushed between steps (256 MiB memset)",
-                   "passes_per_step": statistics.mean(passes) if passes else 0},
+        "config": workload_config(args, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roofline, "issue_roofline": issue, "cpu_baseline": cpu,
+        "roofline": roofline, "cpu_baseline": cpu,
+        "bitexact": bitexact, "target_1e9": target,
         "wall_s_timed_region": wall_s,
+        "passes_per_step": statistics.mean(passes) if passes else 0,
         "breakdown_ms_per_step": {"pilot": sum(pilot_ms) / args.steps, "fold": sum(fold_ms) / args.steps,
-                                  "total_device": sum(dev_ms) / args.steps},
+                                  "total_device": sum(dev_ms) / args.steps,
+                                  "other": (sum(dev_ms) - sum(fold_ms)) / args.steps},
     }
     print(json.dumps(line))
     if dist is not None:
