@@ -383,15 +383,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    merge = os.environ.get("VAXMC_MERGE", "nccl")      # "torch": slab all-reduced from Python (cross-check)
     all_reduce = dmod.make_torch_reducer(dist) if dist else None
+    if dist is not None and merge != "torch":
+        dmod.ensure_comm(ctx, dist)                     # rendezvous only: 128-byte NCCL id over torch.distributed
 
     def one_job(seed):
         cfg = nat.make_config(bounds, N_POP, T_DAYS, n_global, seed, q_lo, q_hi,
                               direct_max=(n_global + 1) if args.direct else 0)
         if world == 1:
             return ctx.run_bounds(cfg)
-        return dmod.run_sharded(dmod.ContextEngine(ctx), cfg, rank, world, all_reduce,
-                                lambda: nat.ResultBuffers(T_DAYS))
+        if merge == "torch":
+            return dmod.run_sharded(dmod.ContextEngine(ctx), cfg, rank, world, all_reduce,
+                                    lambda: nat.ResultBuffers(T_DAYS))
+        return ctx.run_bounds_comm(cfg)      # libvaxmc's own ncclAllReduce, in-stream behind the fold
 
     # ---------------- device-timed leg ("value")
     for i in range(args.warmup):
@@ -402,14 +407,16 @@ def main():
         time.sleep(0.15)
     barrier()
     launches0 = ctx.launch_count
-    dev_ms, fold_ms, pilot_ms, fold_launches, passes = [], [], [], 0, []
+    dev_ms, fold_ms, pilot_ms, merge_ms, fold_launches, passes, fold_samples = [], [], [], [], 0, [], 0
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()                       # L2 flush between timed iterations (outside the events)
         torch.cuda.synchronize()
         out = one_job(2000 + i)
         dev_ms.append(out.c.device_ms); fold_ms.append(out.c.fold_ms); pilot_ms.append(out.c.pilot_ms)
+        merge_ms.append(out.c.merge_ms); fold_samples += out.c.fold_samples
         fold_launches += out.c.fold_launches; passes.append(out.c.n_passes)
+    n_pilot, side_samples = int(out.c.n_pilot), int(out.c.side_samples)
     barrier()
     wall_s = time.perf_counter() - t_wall0
     launches = ctx.launch_count - launches0
@@ -514,7 +521,7 @@ def main():
     counters, cstate = load_counters()
     sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
     issue_peak = N_SM * SCHEDULERS_PER_SM * sm_hz
-    sample_days = args.samples * T_DAYS
+    sample_days = (fold_samples / max(fold_launches, 1)) * T_DAYS     # what one fold launch really stepped
     sd_per_s = sample_days / (fold_ms_avg * 1e-3) if fold_launches else None
     inst_per_launch = traffic = issue_ach = None
     if counters is not None and fold_launches and args.workload == "usa":
@@ -566,8 +573,14 @@ def main():
         "wall_s_timed_region": wall_s,
         "passes_per_step": statistics.mean(passes) if passes else 0,
         "breakdown_ms_per_step": {"pilot": sum(pilot_ms) / args.steps, "fold": sum(fold_ms) / args.steps,
+                                  "merge_allreduce": sum(merge_ms) / args.steps,
                                   "total_device": sum(dev_ms) / args.steps,
-                                  "other": (sum(dev_ms) - sum(fold_ms)) / args.steps},
+                                  "non_fold": (sum(dev_ms) - sum(fold_ms)) / args.steps},
+        "job_split": {"pilot_samples": n_pilot, "side_samples_stepped_beside_the_pilot": side_samples,
+                      "fold_samples_per_launch": fold_samples / max(fold_launches, 1),
+                      "merge": ("single GPU: none" if world == 1 else
+                                "torch.distributed all_reduce from Python" if merge == "torch" else
+                                "ncclAllReduce(uint64 sum) issued by libvaxmc on its own stream")},
     }
     print(json.dumps(line))
     if dist is not None:

@@ -65,7 +65,18 @@ class vx_result(C.Structure):
         ("fold_ms", C.c_double),
         ("pilot_ms", C.c_double),
         ("fold_launches", C.c_int64),
+        ("merge_ms", C.c_double),
+        ("n_pilot", C.c_int64),
+        ("fold_samples", C.c_int64),
+        ("side_samples", C.c_int64),
     ]
+
+
+class vx_nccl_id(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+ABI_VERSION = 2   # include/vaxmc.h: VX_ABI_VERSION
 
 
 # every symbol include/vaxmc.h declares: (restype, argtypes)
@@ -80,6 +91,14 @@ SYMBOLS = {
     "vx_destroy": (None, [_vp]),
     "vx_last_error": (C.c_char_p, [_vp]),
     "vx_version": (C.c_char_p, []),
+    "vx_abi_version": (C.c_int, []),
+    "vx_sizeof": (C.c_int64, [C.c_int]),
+    "vx_comm_unique_id": (C.c_int, [C.POINTER(vx_nccl_id)]),
+    "vx_comm_init": (C.c_int, [_vp, C.POINTER(vx_nccl_id), C.c_int, C.c_int]),
+    "vx_comm_destroy": (C.c_int, [_vp]),
+    "vx_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "vx_run_bounds_comm": (C.c_int, [_vp, _cfgp, _resp]),
+    "vx_host_shard_range": (None, [C.c_int64, C.c_int, C.c_int, _i64p, _i64p]),
     "vx_device_count": (C.c_int, []),
     "vx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
     "vx_trim": (C.c_int, [_vp]),
@@ -132,11 +151,22 @@ def load() -> C.CDLL:
                         f"CPU fallback ({e})") from e
             if nvcc is not None:
                 path = _build.build()   # a compile error must surface, never a stale library
+            else:
+                import warnings
+
+                warnings.warn("libvaxmc.so is older than its sources and nvcc is not available to rebuild it; "
+                              "loading the shipped library (its ABI stamp is checked)")
         L = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)  # AttributeError if the library does not export it
             fn.restype = res
             fn.argtypes = args
+        # the structs are mirrored by hand above: a library built from another header must not be used
+        got = (int(L.vx_abi_version()), int(L.vx_sizeof(0)), int(L.vx_sizeof(1)), int(L.vx_sizeof(2)))
+        want = (ABI_VERSION, C.sizeof(vx_config), C.sizeof(vx_result), C.sizeof(vx_nccl_id))
+        if got != want:
+            raise RuntimeError(f"libvaxmc.so ABI mismatch: library (version, sizeof vx_config, vx_result, "
+                               f"vx_nccl_id) = {got}, this binding expects {want}; rebuild the library")
         _LIB = L
     return _LIB
 
@@ -199,6 +229,7 @@ class Context:
             raise VaxmcError(rc, self._lib.vx_last_error(None).decode())
         self._h = h
         self.device = int(device)
+        self.comm_world = 1
 
     def close(self):
         if getattr(self, "_h", None):
@@ -230,6 +261,27 @@ class Context:
     def run_bounds(self, cfg: vx_config) -> ResultBuffers:
         out = ResultBuffers(cfg.T)
         self._ck(self._lib.vx_run_bounds(self._h, C.byref(cfg), C.byref(out.c)))
+        return out
+
+    # ---- sharded over the ranks of an NCCL communicator owned by the library
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        uid = vx_nccl_id()
+        C.memmove(C.byref(uid), unique_id, 128)
+        self._ck(self._lib.vx_comm_init(self._h, C.byref(uid), int(rank), int(world)))
+        self.comm_world = int(world)
+
+    def comm_destroy(self):
+        self._ck(self._lib.vx_comm_destroy(self._h))
+        self.comm_world = 1
+
+    def comm_info(self):
+        r, w, v = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._lib.vx_comm_info(self._h, C.byref(r), C.byref(w), C.byref(v)))
+        return int(r.value), int(w.value), int(v.value)
+
+    def run_bounds_comm(self, cfg: vx_config) -> ResultBuffers:
+        out = ResultBuffers(cfg.T)
+        self._ck(self._lib.vx_run_bounds_comm(self._h, C.byref(cfg), C.byref(out.c)))
         return out
 
     def run_params(self, cfg: vx_config, params: np.ndarray, want_counts=False):
@@ -329,6 +381,22 @@ class Context:
                                           rk.ctypes.data_as(_i64p), len(rk),
                                           out.ctypes.data_as(_i32p), sums.ctypes.data_as(_i64p)))
         return out, sums
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (one rank makes it, the rendezvous ships it)."""
+    L = load()
+    uid = vx_nccl_id()
+    rc = L.vx_comm_unique_id(C.byref(uid))
+    if rc != VX_OK:
+        raise VaxmcError(rc, L.vx_last_error(None).decode())
+    return bytes(C.string_at(C.byref(uid), 128))
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    f, c = C.c_int64(), C.c_int64()
+    load().vx_host_shard_range(int(n), int(rank), int(world), C.byref(f), C.byref(c))
+    return int(f.value), int(c.value)
 
 
 _CONTEXTS: dict[int, Context] = {}

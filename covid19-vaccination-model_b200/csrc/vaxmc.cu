@@ -20,6 +20,8 @@
 #include "../../include/vaxmc.h"
 #include "vaxmc_kernels.cuh"
 
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -39,6 +41,45 @@ thread_local std::string g_create_error;
 // fixed-point scale of the p_soft_no moments when they travel in the int64 slab: sums of up
 // to 8e9 samples of values in [0,1] stay below 2^63, the mean keeps 9 digits
 constexpr double STATS_FIX = 1073741824.0;   // 2^30
+
+// ---- NCCL, bound at run time -----------------------------------------------------------------
+// The only exchange step of the path is one all-reduce(sum) of the integer slab per pass.  It is
+// issued by the library itself on its own stream, right behind the last fold kernel; libnccl is
+// dlopen'ed (the copy torch already loaded when the process uses torch.distributed for the
+// rendezvous, else the system one), so the library has no link-time dependency on it and
+// single-GPU users never touch it.  Prototypes follow nccl.h 2.x (stable since 2.0).
+struct NcclApi {
+    void *handle = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, vx_nccl_id, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GetVersion)(int *) = nullptr;
+    std::string err;
+};
+constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0;
+
+NcclApi &nccl_api()
+{
+    static NcclApi api;
+    if (api.handle || !api.err.empty()) return api;
+    const char *cands[] = {getenv("VAXMC_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char *c : cands) {
+        if (!c || !*c) continue;
+        api.handle = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) { api.err = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : ""); return api; }
+    auto sym = [&](const char *n) { void *f = dlsym(api.handle, n); if (!f) api.err = std::string("libnccl lacks ") + n; return f; };
+    api.GetUniqueId = (int (*)(void *))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void **, int, vx_nccl_id, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(void *))sym("ncclCommDestroy");
+    api.AllReduce = (int (*)(const void *, void *, size_t, int, int, void *, cudaStream_t))sym("ncclAllReduce");
+    api.GetErrorString = (const char *(*)(int))sym("ncclGetErrorString");
+    api.GetVersion = (int (*)(int *))sym("ncclGetVersion");
+    return api;
+}
 
 struct Target {
     int64_t rank = 0;
@@ -85,6 +126,20 @@ struct Job {
     int n_passes = 0;
     int32_t *d_perm = nullptr;            // pressure-bucket order of the shard (first pass, untimed jobs)
     int64_t perm_first = 0, perm_count = 0;
+    // samples [side_first, side_first+side_count) of the shard are stepped by a DUMP launch on the
+    // side stream WHILE the latency-bound pilot runs (it leaves > 85 % of the SMs idle) and folded
+    // from that matrix once the windows exist, instead of being stepped by the fold kernel later
+    int32_t *d_side = nullptr;
+    int64_t side_first = 0, side_count = 0;
+    bool stats_on_device = false;         // d_stats3 holds this shard's statistics (no host copy yet)
+    double *d_stats3 = nullptr;
+    bool use_comm = false;                // merge the slab with the context's NCCL communicator, in-stream
+    int world = 1;                        // ranks the global sample range is sharded over
+    int64_t fold_samples = 0;             // samples stepped by the streaming-fold launches (pass 1)
+    cudaEvent_t evM0 = nullptr, evM1 = nullptr;
+    double merge_ms = 0.0;
+    bool merge_timed = false;
+    bool fold_timing_pending = false;
     // results (host)
     std::vector<double> mean[4], lower[4], upper[4];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -96,7 +151,8 @@ struct Job {
 } // namespace
 
 enum Slot { SLOT_DUMP = 0, SLOT_ACC, SLOT_WINS, SLOT_TGT, SLOT_RES, SLOT_SEL_RANKS, SLOT_SEL_OUT,
-            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_PERM, SLOT_SORT, SLOT_COUNT };
+            SLOT_SEL_SUMS, SLOT_STATS_PART, SLOT_STATS_MISC, SLOT_PARAMS, SLOT_EXP, SLOT_PERM, SLOT_SORT, SLOT_SIDE, SLOT_TMP_A,
+            SLOT_TMP_B, SLOT_TMP_C, SLOT_COUNT };
 
 struct vx_ctx {
     // grow-only device workspace reused across jobs (cudaMalloc/cudaFree of the pilot matrix
@@ -119,7 +175,11 @@ struct vx_ctx {
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
     int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
+    int64_t side_samples = -1;            // samples stepped beside the pilot (-1: 8 x the pilot, <= 2^18; 0: none)
     int sm_count = 148;
+    // multi-GPU: one NCCL communicator per context (vx_comm_init), used by vx_run_bounds_comm
+    void *comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
 };
 
 namespace {
@@ -196,6 +256,8 @@ void free_job(vx_ctx *ctx)
     if (j->ev1) cudaEventDestroy(j->ev1);
     if (j->evA) cudaEventDestroy(j->evA);
     if (j->evB) cudaEventDestroy(j->evB);
+    if (j->evM0) cudaEventDestroy(j->evM0);
+    if (j->evM1) cudaEventDestroy(j->evM1);
     delete j;
     ctx->job = nullptr;
 }
@@ -457,15 +519,58 @@ int need_device(vx_ctx *ctx)
 }
 
 int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double *d_params,
-                int32_t *d_dump, int64_t ld)
+                int32_t *d_dump, int64_t ld, cudaStream_t st = nullptr, const int32_t *d_perm = nullptr)
 {
+    if (!st) st = ctx->stream;
     SimArgs a = make_args(j, first, count, d_params);
     a.dump = d_dump;
     a.dump_stride = ld;
+    a.perm = d_perm;
     const int64_t grid = (count + SIM_THREADS - 1) / SIM_THREADS;
-    if (ctx->exact_poisson) vx_sim_kernel<SIM_DUMP, 1><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
-    else vx_sim_kernel<SIM_DUMP, 0><<<(unsigned)grid, SIM_THREADS, 0, ctx->stream>>>(a);
+    if (ctx->exact_poisson) vx_sim_kernel<SIM_DUMP, 1><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
+    else vx_sim_kernel<SIM_DUMP, 0><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
     CKL();
+    return VX_OK;
+}
+
+// P(p_pro + p_anti <= 1) for independent uniforms on the two bound intervals: the acceptance
+// probability of model.py:275-287's rejection step (exact area of the box under the line).
+double acceptance_probability(const double *b)
+{
+    const double x0 = std::min(b[0], b[1]), x1 = std::max(b[0], b[1]);
+    const double y0 = std::min(b[2], b[3]), y1 = std::max(b[2], b[3]);
+    if (x1 + y1 <= 1.0) return 1.0;
+    if (x0 + y0 > 1.0) return 0.0;
+    if (x1 == x0 || y1 == y0) {      // degenerate box: a segment (or a point)
+        if (x1 == x0 && y1 == y0) return 1.0;
+        const double lo = (x1 == x0) ? y0 : x0, hi = (x1 == x0) ? y1 : x1, c = 1.0 - ((x1 == x0) ? x0 : y0);
+        return std::min(std::max((c - lo) / (hi - lo), 0.0), 1.0);
+    }
+    // integrate over x the accepted length of y: clamp(1 - x - y0, 0, y1 - y0)
+    const double h = y1 - y0, xa = std::min(std::max(1.0 - y1, x0), x1), xb = std::min(std::max(1.0 - y0, x0), x1);
+    // x in [x0, xa]: full height; x in [xa, xb]: 1 - x - y0 (linear); beyond xb: nothing
+    const double area = (xa - x0) * h + ((1.0 - y0) * (xb - xa) - 0.5 * (xb * xb - xa * xa));
+    return area / ((x1 - x0) * h);
+}
+
+// This shard's rejection count and moments of p_soft_no, left ON THE DEVICE (d_stats3).
+int launch_param_stats(vx_ctx *ctx, Job *j)
+{
+    const int64_t n = j->shard_count, grid = (n + 255) / 256;
+    unsigned long long *d_stop = nullptr;
+    double *d_part = nullptr, *d_out = nullptr;
+    { void *p_ = nullptr; int rc_;
+      rc_ = pool_get(ctx, SLOT_STATS_PART, sizeof(double) * 3 * grid, &p_); if (rc_) return rc_; d_part = (double *)p_;
+      rc_ = pool_get(ctx, SLOT_STATS_MISC, 64, &p_); if (rc_) return rc_; d_stop = (unsigned long long *)p_; d_out = (double *)p_ + 4; }
+    const unsigned long long hstop[2] = {0ull, (unsigned long long)(10 * j->cfg.n_samples)};
+    CK(cudaMemcpyAsync(d_stop, hstop, 16, cudaMemcpyHostToDevice, ctx->stream));
+    Bounds bd;
+    memcpy(bd.b, j->cfg.bounds, sizeof bd.b);
+    vx_param_stats_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(bd, j->cfg.seed, j->shard_first, n, d_stop, d_part);
+    CKL();
+    vx_reduce_stats_kernel<<<1, 1024, 0, ctx->stream>>>(d_part, grid, d_out);
+    CKL();
+    j->d_stats3 = d_out;
     return VX_OK;
 }
 
@@ -557,7 +662,19 @@ int run_expected(vx_ctx *ctx)
 // =====================================================================================
 extern "C" {
 
-const char *vx_version(void) { return "vaxmc 0.1 (sm_100a)"; }
+const char *vx_version(void) { return "vaxmc 0.2 (sm_100a)"; }
+
+int vx_abi_version(void) { return VX_ABI_VERSION; }
+
+int64_t vx_sizeof(int which)
+{
+    switch (which) {
+    case 0: return (int64_t)sizeof(vx_config);
+    case 1: return (int64_t)sizeof(vx_result);
+    case 2: return (int64_t)sizeof(vx_nccl_id);
+    default: return -1;
+    }
+}
 
 int vx_device_count(void)
 {
@@ -601,6 +718,7 @@ void vx_destroy(vx_ctx *ctx)
 {
     if (!ctx) return;
     free_job(ctx);
+    vx_comm_destroy(ctx);
     pool_release(ctx);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->side) cudaStreamDestroy(ctx->side);
@@ -631,6 +749,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "sort_samples") ctx->sort_samples = value != 0;
     else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
     else if (s == "exact_poisson") ctx->exact_poisson = value != 0;
+    else if (s == "side_samples") ctx->side_samples = (int64_t)value;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }
@@ -708,6 +827,8 @@ static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_fir
     CK(cudaEventCreate(&j->ev1));
     CK(cudaEventCreate(&j->evA));
     CK(cudaEventCreate(&j->evB));
+    CK(cudaEventCreate(&j->evM0));
+    CK(cudaEventCreate(&j->evM1));
     CK(cudaEventRecord(j->ev0, ctx->stream));
     return VX_OK;
 }
@@ -734,20 +855,9 @@ int vx_job_param_stats(vx_ctx *ctx, double stats[4])
         stats[0] = 10.0 * (double)j->cfg.n_samples + 1.0;
         return VX_OK;
     }
-    const int64_t n = j->shard_count, grid = (n + 255) / 256;
-    unsigned long long *d_stop = nullptr;
-    double *d_part = nullptr, *d_out = nullptr;
-    { void *p_ = nullptr; int rc_;
-      rc_ = pool_get(ctx, SLOT_STATS_PART, sizeof(double) * 3 * grid, &p_); if (rc_) return rc_; d_part = (double *)p_;
-      rc_ = pool_get(ctx, SLOT_STATS_MISC, 64, &p_); if (rc_) return rc_; d_stop = (unsigned long long *)p_; d_out = (double *)p_ + 4; }
-    const unsigned long long hstop[2] = {0ull, (unsigned long long)(10 * j->cfg.n_samples)};
-    CK(cudaMemcpyAsync(d_stop, hstop, 16, cudaMemcpyHostToDevice, ctx->stream));
-    Bounds bd;
-    memcpy(bd.b, b, sizeof bd.b);
-    vx_param_stats_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(bd, j->cfg.seed, j->shard_first, n, d_stop, d_part);
-    CKL();
-    vx_reduce_stats_kernel<<<1, 1024, 0, ctx->stream>>>(d_part, grid, d_out);
-    CKL();
+    rc = launch_param_stats(ctx, j);
+    if (rc) return rc;
+    double *d_out = j->d_stats3;
     CK(cudaMemcpyAsync(stats, d_out, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
@@ -798,18 +908,41 @@ int vx_job_pilot(vx_ctx *ctx)
         j->n_pilot = 0;
         return plan_windows(ctx, false);
     }
-    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples : default_pilot(j->cfg.q_lo, j->cfg.q_hi, n));
+    // the default size balances the pilot's cost against the fold's, both PER RANK: with the range
+    // sharded over `world` ranks (vx_run_bounds_comm) it is sized from n / world, a value every
+    // rank computes alike, so the replicated pilot does not grow with the GPU count in weak scaling
+    const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples
+                                                     : default_pilot(j->cfg.q_lo, j->cfg.q_hi, std::max<int64_t>(n / j->world, 1)));
     j->n_pilot = np;
-    if (!j->direct && ctx->sort_samples && !j->explicit_params && !(j->cfg.max_running_time > 0.0)) {
-        // the part of the shard the stepper will fold (the pilot's own samples come from its matrix):
-        // sort it now, on the side stream, while the pilot stepper leaves the GPU mostly idle
-        const int64_t lo = std::max(j->shard_first, np), hi = j->shard_first + j->shard_count;
-        if (hi - lo >= 4096 && hi - lo <= ((int64_t)1 << 30)) {
+    if (!j->direct && !(j->cfg.max_running_time > 0.0)) {
+        // the part of the shard the stepper will fold (the pilot's own samples come from its matrix)
+        int64_t lo = std::max(j->shard_first, np);
+        const int64_t hi = j->shard_first + j->shard_count;
+        // (a) its first `side` samples are stepped NOW by a DUMP launch on the side stream: the
+        //     pilot stepper is one serial T-day chain on < 1 CTA per SM, so the GPU is > 85 % idle
+        //     until the windows exist; those rows are folded from their matrix afterwards
+        int64_t side = ctx->side_samples >= 0 ? ctx->side_samples : std::min<int64_t>(8 * np, (int64_t)1 << 18);
+        side = std::min(side, hi - lo);
+        if (side * 4 > hi - lo) side = (hi - lo >= 4096) ? (hi - lo) / 4 : 0;   // never more than a quarter of the shard
+        side &= ~(int64_t)127;
+        if ((double)R * (double)side * 4.0 > 16e9) side = 0;
+        if (side > 0) {
+            void *p_ = nullptr;
+            rc = pool_get(ctx, SLOT_SIDE, sizeof(int32_t) * R * side, &p_);
+            if (rc) return rc;
+            j->d_side = (int32_t *)p_;
+            j->side_first = lo; j->side_count = side;
+            rc = launch_dump(ctx, j, lo, side, j->d_params ? j->d_params + 6 * lo : nullptr, j->d_side, side, ctx->side);
+            if (rc) return rc;
+            lo += side;
+        }
+        // (b) the rest is counting-sorted by pressure bucket (regime sort), also on the side stream
+        if (ctx->sort_samples && !j->explicit_params && hi - lo >= 4096 && hi - lo <= ((int64_t)1 << 30)) {
             rc = launch_regime_sort(ctx, j, lo, hi - lo, ctx->side, &j->d_perm);
             if (rc) return rc;
-            CK(cudaEventRecord(ctx->side_done, ctx->side));
             j->perm_first = lo; j->perm_count = hi - lo;
         }
+        CK(cudaEventRecord(ctx->side_done, ctx->side));
     }
     if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * R * np, &p_); if (rc_) return rc_; j->d_dump = (int32_t *)p_; }
@@ -861,12 +994,15 @@ int vx_job_acc(vx_ctx *ctx, void **device_ptr, int64_t *n_words)
     return VX_OK;
 }
 
-int vx_job_accumulate(vx_ctx *ctx)
+// One streaming pass over this rank's shard.  `sync_end`: the caller merges the slab itself
+// (staged API + an external all-reduce), so the stream must be idle on return; the whole-job
+// entry points pass false and the host does not wait before vx_job_finalize's own copy-back.
+static int accumulate_impl(vx_ctx *ctx, bool sync_end)
 {
     if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
     Job *j = ctx->job;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_accumulate");
-    if (!j->stats_set && !j->lstats_set)
+    if (!j->stats_set && !j->lstats_set && !j->stats_on_device)
         return fail(ctx, VX_ERR_STATE, "vx_job_param_stats (or vx_job_set_param_stats) must precede vx_job_accumulate");
     if (j->aborted) return fail(ctx, VX_ERR_STATE, "job aborted by the rejection rule");
     if (j->direct || j->finished) return VX_OK;
@@ -878,15 +1014,21 @@ int vx_job_accumulate(vx_ctx *ctx)
         // no separate statistics collective: this shard's rejection count and fixed-point moments
         // of p_soft_no ride in header words 2..5 of the slab the ranks all-reduce anyway
         j->stats_in_slab = true;
-        const unsigned long long hs[4] = {
-            (unsigned long long)j->lstats[0], (unsigned long long)std::llround(j->lstats[1] * STATS_FIX),
-            (unsigned long long)std::llround(j->lstats[2] * STATS_FIX), (unsigned long long)j->lstats[3]};
-        CK(cudaMemcpyAsync(j->d_acc + 2, hs, sizeof hs, cudaMemcpyHostToDevice, ctx->stream));
+        if (j->stats_on_device) {
+            vx_stats_to_header_kernel<<<1, 32, 0, ctx->stream>>>(j->d_stats3, (long long)j->shard_count, STATS_FIX, j->d_acc);
+            CKL();
+        } else {
+            const unsigned long long hs[4] = {
+                (unsigned long long)j->lstats[0], (unsigned long long)std::llround(j->lstats[1] * STATS_FIX),
+                (unsigned long long)std::llround(j->lstats[2] * STATS_FIX), (unsigned long long)j->lstats[3]};
+            CK(cudaMemcpyAsync(j->d_acc + 2, hs, sizeof hs, cudaMemcpyHostToDevice, ctx->stream));
+        }
     }
     const bool first_pass = j->n_passes == 0;
     const int64_t todo = first_pass ? j->shard_count : j->shard_done;
     const bool timed = first_pass && j->cfg.max_running_time > 0.0;
     const int64_t chunk = timed ? ctx->chunk_samples : ((int64_t)1 << 30);
+    if (j->d_side || j->d_perm) CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));
     CK(cudaEventRecord(j->evA, ctx->stream));
     // samples of this shard that the pilot already simulated: fold its matrix, not a re-run
     const int64_t lo = j->shard_first, hi = j->shard_first + todo;
@@ -897,6 +1039,13 @@ int vx_job_accumulate(vx_ctx *ctx)
         CKL();
         done = pil_hi - lo;
     }
+    // ... and the samples stepped on the side stream while the pilot ran
+    if (j->d_side && j->side_count > 0 && j->side_first == j->shard_first + done) {
+        vx_fold_matrix_kernel<<<(unsigned)j->R, 256, 0, ctx->stream>>>(j->d_side, j->side_count, 0, j->side_count, j->d_wins, j->d_acc, (int)j->R, j->bins64);
+        CKL();
+        done += j->side_count;
+    }
+    int64_t stepped = 0;
     while (done < todo) {
         const int64_t cnt = std::min(chunk, todo - done);
         SimArgs a = make_args(j, j->shard_first + done, cnt,
@@ -905,7 +1054,6 @@ int vx_job_accumulate(vx_ctx *ctx)
         a.acc = j->d_acc;
         a.bins64 = j->bins64;
         if (j->d_perm && j->perm_first == a.first && j->perm_count == cnt) {
-            CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));
             a.perm = j->d_perm;
         } else if (ctx->sort_samples && !j->explicit_params && cnt >= 4096) {
             int32_t *d_perm = nullptr;
@@ -920,21 +1068,32 @@ int vx_job_accumulate(vx_ctx *ctx)
         CKL();
         j->fold_launches++;
         done += cnt;
+        stepped += cnt;
         if (timed) {
             CK(cudaStreamSynchronize(ctx->stream));
             const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - j->t_begin).count();
             if (el > j->cfg.max_running_time) break;   // model.py:187-189
         }
     }
-    if (first_pass) j->shard_done = done;
+    if (first_pass) { j->shard_done = done; j->fold_samples = stepped; }
     j->n_passes++;
     CK(cudaEventRecord(j->evB, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float fms = 0.f;
-    cudaEventElapsedTime(&fms, j->evA, j->evB);
-    j->fold_ms += fms;
+    j->fold_timing_pending = true;
+    if (j->use_comm && ctx->comm) {
+        // the path's one exchange step: all-reduce(sum) of the integer slab, issued on the stream the
+        // fold ran on, so it starts the moment this rank's last fold CTA retires
+        NcclApi &api = nccl_api();
+        CK(cudaEventRecord(j->evM0, ctx->stream));
+        const int nrc = api.AllReduce(j->d_acc, j->d_acc, (size_t)j->acc_words, NCCL_UINT64, NCCL_SUM, ctx->comm, ctx->stream);
+        if (nrc != 0) return fail(ctx, VX_ERR_CUDA, "ncclAllReduce failed: %s", api.GetErrorString ? api.GetErrorString(nrc) : "?");
+        CK(cudaEventRecord(j->evM1, ctx->stream));
+        j->merge_timed = true;
+    }
+    if (sync_end) CK(cudaStreamSynchronize(ctx->stream));
     return VX_OK;
 }
+
+int vx_job_accumulate(vx_ctx *ctx) { return accumulate_impl(ctx, true); }
 
 int vx_job_finalize(vx_ctx *ctx, vx_result *res)
 {
@@ -943,9 +1102,15 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     int rc = need_device(ctx);
     if (rc) return rc;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_finalize");
-    if (!j->stats_set && !j->lstats_set)
+    if (!j->stats_set && !j->lstats_set && !j->stats_on_device)
         return fail(ctx, VX_ERR_STATE, "vx_job_param_stats (or vx_job_set_param_stats) must precede vx_job_finalize");
     if (!j->stats_set && j->direct) {       // a direct job without a statistics collective: local == global
+        if (!j->lstats_set && j->stats_on_device) {
+            CK(cudaMemcpyAsync(j->lstats, j->d_stats3, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            j->lstats[3] = (double)j->shard_count;
+            j->lstats_set = true;
+        }
         memcpy(j->gstats, j->lstats, sizeof j->gstats);
         j->stats_set = true;
         j->aborted = j->gstats[0] > 10.0 * (double)j->cfg.n_samples;
@@ -963,6 +1128,12 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
         CK(cudaMemcpyAsync(sums.data(), j->d_acc + ACC_HDR, sizeof(long long) * R, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(hdr, j->d_acc, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (j->fold_timing_pending) {
+            float fms = 0.f;
+            if (cudaEventElapsedTime(&fms, j->evA, j->evB) == cudaSuccess) j->fold_ms += fms;
+            if (j->merge_timed && cudaEventElapsedTime(&fms, j->evM0, j->evM1) == cudaSuccess) j->merge_ms += fms;
+            j->fold_timing_pending = j->merge_timed = false;
+        }
         const int64_t n = (int64_t)hdr[0];
         if (n < 1) return fail(ctx, VX_ERR_STATE, "no samples were folded");
         if (j->stats_in_slab) {
@@ -970,7 +1141,8 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
             j->gstats[2] = (double)hdr[4] / STATS_FIX; j->gstats[3] = (double)hdr[5];
             j->aborted = j->gstats[0] > 10.0 * (double)j->cfg.n_samples;      // model.py:282-287
             if (j->aborted) {
-                res->device_ms = res->fold_ms = res->pilot_ms = 0; res->fold_launches = 0;
+                res->device_ms = res->fold_ms = res->pilot_ms = res->merge_ms = 0; res->fold_launches = 0;
+                res->n_pilot = res->fold_samples = res->side_samples = 0;
                 j->n_total = 0;
                 fill_result_scalars(ctx, res);
                 return VX_OK;
@@ -1028,6 +1200,10 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     res->fold_ms = j->fold_ms;
     res->pilot_ms = j->pilot_ms;
     res->fold_launches = j->fold_launches;
+    res->merge_ms = j->merge_ms;
+    res->n_pilot = j->n_pilot;
+    res->fold_samples = j->fold_samples;
+    res->side_samples = j->side_count;
     fill_result_scalars(ctx, res);
     return copy_results(ctx, res);
 }
@@ -1045,14 +1221,35 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
     Job *j = ctx->job;
     int rc;
     if (!j->explicit_params) {
-        double st[4];
-        rc = vx_job_param_stats(ctx, st);
-        if (rc) return rc;
-        if (vx_job_set_param_stats(ctx, st) == 1) {
-            res->device_ms = 0; res->fold_ms = 0; res->pilot_ms = 0; res->fold_launches = 0;
-            fill_result_scalars(ctx, res);
-            res->n_finished = 0;
-            return VX_OK;
+        // Rejection statistics of the parameter draw.  When most of the (p_pro, p_anti) box is
+        // acceptable the 10*n_rep abort cannot trigger and nothing downstream waits for the
+        // numbers: the kernels run asynchronously and their result travels in the slab header
+        // (streamed job) or is read with the final copy-back (direct job).  Otherwise (a box that is
+        // mostly or wholly infeasible) they are read first, as the reference does, so that a job that
+        // is going to abort does not run its pilot with millions of rejection attempts per sample.
+        if (acceptance_probability(j->cfg.bounds) >= 0.25 && j->shard_count > 0) {
+            rc = need_device(ctx);
+            if (rc) return rc;
+            rc = launch_param_stats(ctx, j);
+            if (rc) return rc;
+            j->stats_on_device = true;
+        } else {
+            double st[4];
+            rc = vx_job_param_stats(ctx, st);
+            if (rc) return rc;
+            // a sharded job decides on the MERGED count (slab header) unless no pair is acceptable at
+            // all, which every rank sees alike; a single-GPU job knows the global count already
+            const bool certain = st[0] > 10.0 * (double)j->cfg.n_samples &&
+                                 (!j->use_comm || acceptance_probability(j->cfg.bounds) == 0.0);
+            if ((!j->use_comm || j->direct) ? vx_job_set_param_stats(ctx, st) == 1 : certain) {
+                j->aborted = true;
+                memcpy(j->gstats, st, sizeof st);
+                res->device_ms = 0; res->fold_ms = 0; res->pilot_ms = 0; res->merge_ms = 0; res->fold_launches = 0;
+                res->n_pilot = res->fold_samples = res->side_samples = 0;
+                fill_result_scalars(ctx, res);
+                res->n_finished = 0;
+                return VX_OK;
+            }
         }
     }
     rc = vx_job_pilot(ctx);
@@ -1063,7 +1260,7 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
         CK(cudaStreamSynchronize(ctx->stream));
     }
     for (int it = 0; it < 64; ++it) {
-        rc = vx_job_accumulate(ctx);
+        rc = accumulate_impl(ctx, false);
         if (rc) return rc;
         rc = vx_job_finalize(ctx, res);
         if (rc != VX_REFINE) return rc;
@@ -1076,6 +1273,80 @@ int vx_run_bounds(vx_ctx *ctx, const vx_config *cfg, vx_result *res)
     if (!ctx || !res) return VX_ERR_ARG;
     int rc = job_begin_common(ctx, cfg, 0, cfg ? cfg->n_samples : 0, nullptr);
     if (rc == VX_OK) rc = run_job(ctx, res, nullptr);
+    const std::string keep = ctx->err;
+    free_job(ctx);
+    ctx->err = keep;
+    return rc;
+}
+
+// ---- multi-GPU: one rank of a job sharded over the ranks of the context's communicator -------
+int vx_comm_unique_id(vx_nccl_id *out)
+{
+    if (!out) return VX_ERR_ARG;
+    NcclApi &api = nccl_api();
+    if (!api.err.empty()) return fail(nullptr, VX_ERR_STATE, "NCCL unavailable: %s", api.err.c_str());
+    const int nrc = api.GetUniqueId(out);
+    if (nrc != 0) return fail(nullptr, VX_ERR_CUDA, "ncclGetUniqueId failed: %s", api.GetErrorString(nrc));
+    return VX_OK;
+}
+
+int vx_comm_init(vx_ctx *ctx, const vx_nccl_id *id, int rank, int world)
+{
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return fail(ctx, VX_ERR_ARG, "bad communicator arguments");
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    if (ctx->comm) return fail(ctx, VX_ERR_STATE, "the context already has a communicator");
+    NcclApi &api = nccl_api();
+    if (!api.err.empty()) return fail(ctx, VX_ERR_STATE, "NCCL unavailable: %s", api.err.c_str());
+    void *comm = nullptr;
+    const int nrc = api.CommInitRank(&comm, world, *id, rank);
+    if (nrc != 0) return fail(ctx, VX_ERR_CUDA, "ncclCommInitRank failed: %s", api.GetErrorString(nrc));
+    ctx->comm = comm; ctx->comm_rank = rank; ctx->comm_world = world;
+    return VX_OK;
+}
+
+int vx_comm_destroy(vx_ctx *ctx)
+{
+    if (!ctx) return VX_ERR_ARG;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api().CommDestroy(ctx->comm);
+    }
+    ctx->comm = nullptr; ctx->comm_rank = 0; ctx->comm_world = 1;
+    return VX_OK;
+}
+
+int vx_comm_info(vx_ctx *ctx, int *rank, int *world, int *nccl_version)
+{
+    if (!ctx) return VX_ERR_ARG;
+    if (rank) *rank = ctx->comm_rank;
+    if (world) *world = ctx->comm ? ctx->comm_world : 1;
+    if (nccl_version) { *nccl_version = 0; NcclApi &api = nccl_api(); if (api.err.empty() && api.GetVersion) api.GetVersion(nccl_version); }
+    return VX_OK;
+}
+
+void vx_host_shard_range(int64_t n, int rank, int world, int64_t *first, int64_t *count)
+{
+    const int64_t base = n / world, rem = n % world;
+    if (first) *first = (int64_t)rank * base + std::min<int64_t>(rank, rem);
+    if (count) *count = base + (rank < rem ? 1 : 0);
+}
+
+int vx_run_bounds_comm(vx_ctx *ctx, const vx_config *cfg, vx_result *res)
+{
+    if (!ctx || !res || !cfg) return VX_ERR_ARG;
+    if (!ctx->comm || ctx->comm_world == 1) return vx_run_bounds(ctx, cfg, res);
+    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 65536;
+    const bool direct = cfg->mode == VX_MODE_EXPECTED || cfg->n_samples <= dmax;
+    int64_t first = 0, count = cfg->n_samples;
+    if (!direct) vx_host_shard_range(cfg->n_samples, ctx->comm_rank, ctx->comm_world, &first, &count);
+    int rc = job_begin_common(ctx, cfg, first, count, nullptr);
+    if (rc == VX_OK) {
+        ctx->job->use_comm = !direct;     // a direct job is computed whole on every rank: no collective
+        ctx->job->world = ctx->comm_world;
+        rc = run_job(ctx, res, nullptr);
+    }
     const std::string keep = ctx->err;
     free_job(ctx);
     ctx->err = keep;

@@ -356,6 +356,20 @@ __global__ void __launch_bounds__(1024) vx_reduce_stats_kernel(const double *blo
     if (threadIdx.x < 3) out3[threadIdx.x] = sh[threadIdx.x][0];
 }
 
+// This shard's statistics (vx_reduce_stats_kernel's out3 = rejections, sum s, sum s^2) into header
+// words 2..5 of the accumulator slab as integers / fixed point, so that they are merged by the
+// same all-reduce as the histograms and never visit the host on their own.
+__global__ void vx_stats_to_header_kernel(const double *out3, long long count, double fix,
+                                          unsigned long long *acc)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        acc[2] = (unsigned long long)out3[0];
+        acc[3] = (unsigned long long)llround(out3[1] * fix);
+        acc[4] = (unsigned long long)llround(out3[2] * fix);
+        acc[5] = (unsigned long long)count;
+    }
+}
+
 // Parameter tuples as drawn on the device, for sample_param_combinations' return value.
 __global__ void __launch_bounds__(256) vx_sample_params_kernel(Bounds bd, uint64_t seed,
                                                                int64_t first, int64_t count,
@@ -451,9 +465,9 @@ struct SimArgs {
     int64_t count;          // samples in this launch
     int64_t N;
     int T, W;
-    int32_t *dump;          // DUMP: [R][dump_stride] raw rows, column = local sample
+    int32_t *dump;          // DUMP: [R][dump_stride] raw rows, column = position in this launch
     int64_t dump_stride;
-    const int32_t *perm;    // FOLD: optional order of the local samples (pressure-sorted), or nullptr
+    const int32_t *perm;    // optional order of the local samples (pressure-sorted): position -> local id, or nullptr
     const Win *wins;        // FOLD: [R][2]
     unsigned long long *acc;// FOLD: header(8) | sums[R] | below[R][2] | hist bins
     int bins64;             // FOLD: histogram bins are 64-bit words (global n >= 2^32), else 32-bit
@@ -503,8 +517,8 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
     if (warp_base >= a.count) return;                       // warp-uniform
     const int nvalid = (int)min((int64_t)32, a.count - warp_base);
     const bool live = lane < nvalid;
-    int64_t local = warp_base + (live ? lane : nvalid - 1);  // dead lanes shadow a live one
-    if (MODE == SIM_FOLD && a.perm) local = a.perm[local];
+    const int64_t col = warp_base + (live ? lane : nvalid - 1);   // dead lanes shadow a live one
+    const int64_t local = a.perm ? (int64_t)a.perm[col] : col;    // position -> local sample id
     const uint64_t sample = (uint64_t)(a.first + local);
     const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
     const uint32_t s_lo = (uint32_t)sample, s_hi = (uint32_t)(sample >> 32);
@@ -578,12 +592,12 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                 }
             } else if (live) {
                 const int64_t ld = a.dump_stride;
-                a.dump[(int64_t)day * ld + local] = n_vacc;
-                a.dump[((int64_t)T + 2 * W + day) * ld + local] = stock;
+                a.dump[(int64_t)day * ld + col] = n_vacc;
+                a.dump[((int64_t)T + 2 * W + day) * ld + col] = stock;
                 if (week0) {
                     const int k = day / 7;
-                    a.dump[((int64_t)T + k) * ld + local] = dv + q0;
-                    a.dump[((int64_t)T + W + k) * ld + local] = n_vacc + stock;
+                    a.dump[((int64_t)T + k) * ld + col] = dv + q0;
+                    a.dump[((int64_t)T + W + k) * ld + col] = n_vacc + stock;
                 }
             }
             return dv;

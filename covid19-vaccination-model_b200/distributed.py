@@ -8,8 +8,10 @@ windows, window histograms; the shard's rejection count and the fixed-point mome
 p_soft_no, model.py:280-287, 339-342, ride in its header) -- integer addition, hence results
 that are bit-identical for 1/2/4/8 GPUs.
 
-torch.distributed is plumbing only (process group + the NCCL call on a tensor that aliases
-the library's device slab); all arithmetic is in libvaxmc.so.
+torch.distributed is plumbing only: it ships the 128-byte NCCL unique id once per process
+(ensure_comm); the collective itself is libvaxmc's own ncclAllReduce on its own stream
+(vx_run_bounds_comm).  run_sharded + the staged vx_job_* calls remain as the backend-agnostic
+driver (gloo tests, VAXMC_MERGE=torch); all arithmetic is in libvaxmc.so.
 """
 from __future__ import annotations
 
@@ -198,5 +200,22 @@ def run_job(cfg, device=None):
     ctx = nat.default_context(int(device))
     if world == 1:
         return ctx.run_bounds(cfg)
-    return run_sharded(ContextEngine(ctx), cfg, dist.get_rank(), world, make_torch_reducer(dist),
-                       lambda: nat.ResultBuffers(cfg.T))
+    if os.environ.get("VAXMC_MERGE", "nccl") == "torch":
+        # the slab merged by torch.distributed from Python (two host synchronisations around it):
+        # kept for backends without NCCL and as the cross-check of the in-library path
+        return run_sharded(ContextEngine(ctx), cfg, dist.get_rank(), world, make_torch_reducer(dist),
+                           lambda: nat.ResultBuffers(cfg.T))
+    ensure_comm(ctx, dist)
+    return ctx.run_bounds_comm(cfg)
+
+
+def ensure_comm(ctx, dist):
+    """Give the context its NCCL communicator (once): rank 0 makes the unique id through the
+    library, torch.distributed ships the 128 bytes -- rendezvous is all torch does on this path;
+    the all-reduce itself is issued by libvaxmc on its own stream, right behind the fold."""
+    world = dist.get_world_size()
+    if ctx.comm_world == world:
+        return
+    box = [nat.comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], dist.get_rank(), world)

@@ -49,6 +49,7 @@ extern "C" {
 #endif
 
 #define VX_SERIES 4
+#define VX_ABI_VERSION 2 /* bumped whenever vx_config / vx_result / a signature changes */
 
 enum {
     VX_OK = 0,
@@ -94,20 +95,34 @@ typedef struct vx_result {
     double fold_ms;          /* of which: streaming-fold stepper launches (all passes)        */
     double pilot_ms;         /* of which: pilot/direct stepper + radix select                 */
     int64_t fold_launches;   /* number of streaming-fold launches behind fold_ms              */
+    double merge_ms;         /* of which: the NCCL all-reduce of the slab (vx_run_bounds_comm) */
+    int64_t n_pilot;         /* samples of the replicated pilot (0: direct job)               */
+    int64_t fold_samples;    /* samples this rank's fold launches stepped in the first pass   */
+    int64_t side_samples;    /* samples stepped beside the pilot and folded from their matrix */
 } vx_result;
+
+/* ncclUniqueId, byte for byte (nccl.h: 128 bytes).  Made by ONE rank (vx_comm_unique_id), shipped
+ * to the others by whatever rendezvous the host program has (torch.distributed, MPI, a file). */
+typedef struct vx_nccl_id { char internal[128]; } vx_nccl_id;
 
 /* ---- lifetime ------------------------------------------------------------------- */
 int vx_create(vx_ctx **out, int device);
 void vx_destroy(vx_ctx *ctx);
 const char *vx_last_error(vx_ctx *ctx); /* ctx may be NULL: last error of vx_create  */
 const char *vx_version(void);
+/* ABI stamp for bindings that mirror the structs by hand (ctypes): VX_ABI_VERSION of the built
+ * library and sizeof(vx_config) [0], sizeof(vx_result) [1], sizeof(vx_nccl_id) [2].          */
+int vx_abi_version(void);
+int64_t vx_sizeof(int which);
 int vx_device_count(void);              /* 0 when no CUDA device is usable            */
 /* tuning knobs (mainly for tests): "max_bins" (bins per window, default 262144),
  * "pilot_sigmas" (half-width of the pilot bracket in rank sigmas, default 6),
  * "use_pilot" (0: start from the coarse full-range windows), "sort_samples" (0: fold the
  * shard in id order instead of pressure-bucket order; same integers either way), "chunk_samples"
  * (granularity of the max_running_time check, default 2^20), "exact_poisson" (1: validation
- * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; ~3x slower). */
+ * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; ~11x slower),
+ * "side_samples" (samples stepped on a side stream while the pilot runs and folded from their
+ * matrix; -1 = default 8 x pilot, 0 = none; same integers either way).                       */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
  * vx_trim returns it to the driver. */
@@ -115,6 +130,23 @@ int vx_trim(vx_ctx *ctx);
 
 /* ---- whole job on one GPU (run_sampling, model.py:139-228, + parameter draw 231-303) */
 int vx_run_bounds(vx_ctx *ctx, const vx_config *cfg, vx_result *res);
+
+/* ---- the same job sharded over the GPUs of one box (run_sampling's sample loop, model.py:176-189,
+ * split by global sample id; the per-date reduction of model.py:216-228 after the merge) ------
+ * One process per GPU.  vx_comm_unique_id on one rank, the 128 bytes to every rank, then
+ * vx_comm_init(ctx, id, rank, world) on each (collective: ncclCommInitRank).  vx_run_bounds_comm
+ * is then called by EVERY rank with the same cfg: rank r steps the contiguous shard
+ * vx_host_shard_range(n, r, world), the integer slab is merged by ONE ncclAllReduce(sum) per pass
+ * issued by the library on its own stream right behind the fold, and every rank returns the same
+ * (bit-identical, world-independent) result.  Jobs with n_samples <= direct_max run whole on each
+ * rank without a collective.  libnccl.so.2 is dlopen'ed on first use ($VAXMC_NCCL_LIB overrides).
+ * Without a communicator (or world == 1) vx_run_bounds_comm == vx_run_bounds.                  */
+int vx_comm_unique_id(vx_nccl_id *out);
+int vx_comm_init(vx_ctx *ctx, const vx_nccl_id *id, int rank, int world);
+int vx_comm_destroy(vx_ctx *ctx);
+int vx_comm_info(vx_ctx *ctx, int *rank, int *world, int *nccl_version);
+int vx_run_bounds_comm(vx_ctx *ctx, const vx_config *cfg, vx_result *res);
+void vx_host_shard_range(int64_t n, int rank, int world, int64_t *first, int64_t *count);
 
 /* Same reduction over EXPLICIT parameter tuples, params = host [n][6] row-major in the
  * reference's tuple order (model.py:296-300).  cfg->bounds is ignored, cfg->n_samples = n.

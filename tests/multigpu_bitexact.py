@@ -4,9 +4,12 @@ bit-identical to the single-GPU result.
 
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/multigpu_bitexact.py
 
-Every rank runs the sharded job through run_model (one NCCL all-reduce of the integer slab);
-rank 0 additionally runs the same job alone on its GPU through the single-GPU entry point and
-compares every array with np.array_equal.  Prints one JSON line per scenario.
+Every rank runs the sharded job through run_model (one ncclAllReduce of the integer slab, issued
+by libvaxmc on its own stream); rank 0 additionally runs the same job alone on its GPU through
+the single-GPU entry point and compares every array with np.array_equal.  Also: the same job
+with the slab merged by torch.distributed from Python (VAXMC_MERGE=torch) gives the same bytes,
+an entropy seed (seed=None) is rank 0's on every rank, and an infeasible parameter box aborts on
+every rank without a hang.  Prints one JSON line per scenario; exit code 0 iff all are ok.
 """
 import importlib
 import json
@@ -62,6 +65,45 @@ def main():
             print(json.dumps({"scenario": name, "n_gpus": world, "bit_identical_to_single_gpu": equal,
                               "identical_on_all_ranks": same_across_ranks, "passes": int(single.c.n_passes),
                               "agnostics": msg, "ok": ok}))
+    usa = ([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10])
+    dates = dict(start_date="2020-12-15", end_date="2022-07-1")
+
+    def digest_of(res):
+        return float(sum(res[k][f].sum() for k in vax.SERIES for f in ("mean", "lower", "upper")))
+
+    def same_on_all_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+        lo, hi = t.clone(), t.clone()
+        if world > 1:
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return bool(lo.item() == hi.item())
+
+    # (a) the Python-driven merge (torch.distributed all_reduce on the slab) gives the same bytes
+    a_res, _, _ = vax.run_model(*usa, 95, 500_000, 50000, dates, seed=77)
+    os.environ["VAXMC_MERGE"] = "torch"
+    vax.cache_clear()
+    b_res, _, _ = vax.run_model(*usa, 95, 500_000, 50000, dates, seed=77)
+    del os.environ["VAXMC_MERGE"]
+    eq = all(np.array_equal(a_res[k][f], b_res[k][f]) for k in vax.SERIES for f in ("mean", "lower", "upper"))
+    ok = eq and same_on_all_ranks(digest_of(a_res))
+    ok_all = ok_all and ok
+    if rank == 0:
+        print(json.dumps({"scenario": "in-library ncclAllReduce == torch.distributed all_reduce of the slab",
+                          "n_gpus": world, "ok": ok}))
+    # (b) seed=None (the reference's default call): one key for the whole job
+    vax.seed(None)
+    c_res, c_err, _ = vax.run_model(*usa, 95, 300_000, 50000, dates)
+    ok = c_err == "" and c_res["number_finished_samples"] == 300_000 and same_on_all_ranks(digest_of(c_res))
+    ok_all = ok_all and ok
+    if rank == 0:
+        print(json.dumps({"scenario": "entropy seed (seed=None): identical bands on every rank", "n_gpus": world, "ok": ok}))
+    # (c) a parameter box with no acceptable (pro, anti) pair, and one that is almost infeasible
+    for name, pro, anti in (("infeasible box", [70, 90], [50, 60]), ("almost infeasible box (abort by the merged count)", [60, 99], [38, 99])):
+        d_res, d_err, d_msg = vax.run_model(pro, anti, [0, 0.1], [3, 4], [0.2, 0.24], [10, 10], 95, 200_000, 50000, dates, seed=3)
+        ok = d_res is None and d_err.startswith("ERROR: The pertentages") and same_on_all_ranks(1.0 if d_res is None else 0.0)
+        ok_all = ok_all and ok
+        if rank == 0:
+            print(json.dumps({"scenario": name + ": every rank aborts, nobody hangs", "n_gpus": world, "ok": ok}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -30,7 +30,23 @@ def test_struct_layout_matches_header(vax):
     nat = vax._native
     # vx_config: 12 doubles + i64 + 2*i32 + i64 + u64 + 2 doubles + 2*i64 + double
     assert ctypes.sizeof(nat.vx_config) == 12 * 8 + 8 + 4 + 4 + 8 + 8 + 16 + 16 + 8
-    assert ctypes.sizeof(nat.vx_result) == 12 * 8 + 8 + 8 + 16 + 4 + 4 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(nat.vx_result) == 12 * 8 + 8 + 8 + 16 + 4 + 4 + 8 + 8 + 8 + 8 + 8 + 3 * 8
+    # ... and the built library agrees (the stamp _native.load() checks before handing the library out)
+    lib = nat.load()
+    assert lib.vx_abi_version() == nat.ABI_VERSION
+    hdr = open(os.path.join(ROOT, "include", "vaxmc.h")).read()
+    assert int(re.search(r"#define VX_ABI_VERSION (\d+)", hdr).group(1)) == nat.ABI_VERSION
+    assert lib.vx_sizeof(0) == ctypes.sizeof(nat.vx_config)
+    assert lib.vx_sizeof(1) == ctypes.sizeof(nat.vx_result)
+    assert lib.vx_sizeof(2) == ctypes.sizeof(nat.vx_nccl_id) == 128
+
+
+def test_shard_range_matches_python_driver(vax):
+    """vx_host_shard_range (what vx_run_bounds_comm shards by) == distributed.shard_range."""
+    for n in (0, 1, 7, 1000, 10**9 + 7):
+        for world in (1, 2, 3, 8):
+            for r in range(world):
+                assert vax._native.shard_range(n, r, world) == vax.distributed.shard_range(n, r, world)
 
 
 def test_library_is_sm100a_only(vax):
