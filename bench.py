@@ -270,10 +270,10 @@ def run_grid(args, vax, ctx, rank, world, local_rank, dist):
                  boxes[b]["nvmax"]) for b in mine]
 
     def one_pass(seed0):
-        # the product's batched entry point: 2 host threads / contexts per GPU overlap one
-        # scenario's latency-bound pilot with the other's fold
+        # the product's batched entry point: ONE library call per rank (vx_run_grid) pipelines the
+        # boxes -- next boxes' pilots in the shadow of the current boxes' folds
         res = vax.run_model_grid(box_args, ci, args.samples, N_POP, DATES, seeds=[seed0 + b for b in mine],
-                                 device=local_rank, workers=args.grid_workers)
+                                 device=local_rank, wave=args.grid_wave)
         checksum = 0.0
         for r, err, msg in res:
             assert err == ""
@@ -308,7 +308,7 @@ def run_grid(args, vax, ctx, rank, world, local_rank, dist):
                                    "CI=%g, boxes partitioned over ranks" % (args.boxes, args.samples, ci),
                        "boxes": args.boxes, "samples_per_box": args.samples, "days": T_DAYS, "N": N_POP,
                        "generator": "bench.grid_boxes(seed=20261019)"},
-            "grid_workers": args.grid_workers, "gpu_launches_ctx0": ctx.launch_count - l0,
+            "grid_wave": args.grid_wave, "gpu_launches": ctx.launch_count - l0,
             "timing": "host wall clock around the whole grid incl. D2H of every box's bands (max over ranks)"}))
     if dist is not None:
         dist.destroy_process_group()
@@ -326,7 +326,7 @@ def main():
     ap.add_argument("--workload", default="usa", choices=["usa", "wide5y", "grid"],
                     help="usa: configs[1]/[2] (use --samples for 1e9/N); wide5y: configs[3]; grid: configs[4]")
     ap.add_argument("--boxes", type=int, default=1024, help="grid workload: number of bound boxes")
-    ap.add_argument("--grid-workers", type=int, default=2, help="grid workload: host threads/contexts per GPU")
+    ap.add_argument("--grid-wave", type=int, default=0, help="grid workload: boxes in flight per pipeline stage (0: library default)")
     ap.add_argument("--ci", type=float, default=None, help="CI in percent (default 95; grid: 99)")
     ap.add_argument("--direct", action="store_true",
                     help="force the materialise + radix-select path (HBM-bound passes) instead of the streaming fold")

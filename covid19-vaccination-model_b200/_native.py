@@ -98,6 +98,7 @@ SYMBOLS = {
     "vx_comm_destroy": (C.c_int, [_vp]),
     "vx_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "vx_run_bounds_comm": (C.c_int, [_vp, _cfgp, _resp]),
+    "vx_run_grid": (C.c_int, [_vp, _cfgp, C.c_int32, _resp, C.c_int32]),
     "vx_host_shard_range": (None, [C.c_int64, C.c_int, C.c_int, _i64p, _i64p]),
     "vx_device_count": (C.c_int, []),
     "vx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_double]),
@@ -283,6 +284,19 @@ class Context:
         out = ResultBuffers(cfg.T)
         self._ck(self._lib.vx_run_bounds_comm(self._h, C.byref(cfg), C.byref(out.c)))
         return out
+
+    def run_grid(self, cfgs, wave: int = 0) -> list:
+        """A batch of independent jobs (bound boxes) pipelined on this GPU: list of ResultBuffers."""
+        n = len(cfgs)
+        outs = [ResultBuffers(c.T) for c in cfgs]
+        carr = (vx_config * n)(*cfgs)
+        rarr = (vx_result * n)()
+        for i, o in enumerate(outs):
+            C.memmove(C.byref(rarr[i]), C.byref(o.c), C.sizeof(vx_result))
+        self._ck(self._lib.vx_run_grid(self._h, carr, n, rarr, int(wave)))
+        for i, o in enumerate(outs):
+            C.memmove(C.byref(o.c), C.byref(rarr[i]), C.sizeof(vx_result))
+        return outs
 
     def run_params(self, cfg: vx_config, params: np.ndarray, want_counts=False):
         params = np.ascontiguousarray(params, dtype=np.float64).reshape(-1, 6)

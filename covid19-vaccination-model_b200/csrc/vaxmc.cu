@@ -140,6 +140,10 @@ struct Job {
     double merge_ms = 0.0;
     bool merge_timed = false;
     bool fold_timing_pending = false;
+    bool stats_fetch_pending = false;
+    int pilot_stage = 0;                  // 0 idle, 1 expected-value job done, 2 pilot in flight, 3 no pilot: plan from bounds
+    cudaStream_t pilot_stream = nullptr;
+    std::vector<int64_t> pilot_ranks;     // the 4 pilot ranks whose order statistics bracket the two quantiles
     // results (host)
     std::vector<double> mean[4], lower[4], upper[4];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evA = nullptr, evB = nullptr;
@@ -175,8 +179,13 @@ struct vx_ctx {
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
     int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
-    int64_t side_samples = -1;            // samples stepped beside the pilot (-1: 8 x the pilot, <= 2^18; 0: none)
+    int64_t side_samples = -1;            // samples stepped beside the pilot (-1: 2 x the pilot, <= 2^18; 0: none)
     int sm_count = 148;
+    // pinned host staging for the copy-backs (a D2H copy into pageable memory blocks the host
+    // until it is done, which would serialise the batched grid driver)
+    void *hpin[2] = {nullptr, nullptr};
+    size_t hpin_cap[2] = {0, 0};
+    std::vector<vx_ctx *> subs;           // vx_run_grid: one sub-context (streams + workspace + job) per box in flight
     // multi-GPU: one NCCL communicator per context (vx_comm_init), used by vx_run_bounds_comm
     void *comm = nullptr;
     int comm_rank = 0, comm_world = 1;
@@ -226,9 +235,30 @@ int pool_get(vx_ctx *ctx, Slot slot, size_t bytes, void **out)
     return VX_OK;
 }
 
+enum HSlot { HSLOT_SEL = 0, HSLOT_FIN = 1 };
+
+int hpin_get(vx_ctx *ctx, HSlot slot, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 64;
+    if (ctx->hpin_cap[slot] < bytes) {
+        if (ctx->hpin[slot]) CK(cudaFreeHost(ctx->hpin[slot]));
+        ctx->hpin[slot] = nullptr; ctx->hpin_cap[slot] = 0;
+        CK(cudaMallocHost(&ctx->hpin[slot], bytes + bytes / 4));
+        ctx->hpin_cap[slot] = bytes + bytes / 4;
+    }
+    *out = ctx->hpin[slot];
+    return VX_OK;
+}
+
 void pool_release(vx_ctx *ctx)
 {
     cudaSetDevice(ctx->device);
+    for (vx_ctx *sub : ctx->subs) vx_destroy(sub);
+    ctx->subs.clear();
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->hpin[i]) cudaFreeHost(ctx->hpin[i]);
+        ctx->hpin[i] = nullptr; ctx->hpin_cap[i] = 0;
+    }
     for (int i = 0; i < SLOT_COUNT; ++i) {
         if (ctx->pool[i]) cudaFree(ctx->pool[i]);
         ctx->pool[i] = nullptr;
@@ -486,28 +516,46 @@ int plan_windows(vx_ctx *ctx, bool from_pilot)
     return VX_OK;
 }
 
-int run_select_i32(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, int64_t n,
-                   const std::vector<int64_t> &ranks, std::vector<int64_t> &ord,
-                   std::vector<long long> &sums)
+// Exact order statistics + row sums of an int32 matrix: launch (kernel + copy-back into pinned
+// host memory, all asynchronous on `st`) and collect (once `st` has been synchronised).
+int select_launch(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, int64_t n,
+                  const std::vector<int64_t> &ranks, cudaStream_t st)
 {
     const int K = (int)ranks.size();
     int64_t *d_ranks = nullptr;
     int32_t *d_out = nullptr;
     long long *d_sums = nullptr;
+    void *h = nullptr;
     { void *p_ = nullptr; int rc_;
       rc_ = pool_get(ctx, SLOT_SEL_RANKS, sizeof(int64_t) * K, &p_); if (rc_) return rc_; d_ranks = (int64_t *)p_;
       rc_ = pool_get(ctx, SLOT_SEL_OUT, sizeof(int32_t) * rows * K, &p_); if (rc_) return rc_; d_out = (int32_t *)p_;
-      rc_ = pool_get(ctx, SLOT_SEL_SUMS, sizeof(long long) * rows, &p_); if (rc_) return rc_; d_sums = (long long *)p_; }
-    CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, ctx->stream));
-    vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, ctx->stream>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
+      rc_ = pool_get(ctx, SLOT_SEL_SUMS, sizeof(long long) * rows, &p_); if (rc_) return rc_; d_sums = (long long *)p_;
+      rc_ = hpin_get(ctx, HSLOT_SEL, sizeof(long long) * rows + sizeof(int32_t) * rows * K, &h); if (rc_) return rc_; }
+    CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, st));
+    vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
     CKL();
-    std::vector<int32_t> ho(rows * K);
-    sums.resize(rows);
-    CK(cudaMemcpyAsync(ho.data(), d_out, sizeof(int32_t) * rows * K, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(sums.data(), d_sums, sizeof(long long) * rows, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpyAsync(h, d_sums, sizeof(long long) * rows, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync((char *)h + sizeof(long long) * rows, d_out, sizeof(int32_t) * rows * K, cudaMemcpyDeviceToHost, st));
+    return VX_OK;
+}
+
+void select_collect(vx_ctx *ctx, int64_t rows, int K, std::vector<int64_t> &ord, std::vector<long long> &sums)
+{
+    const long long *hs = (const long long *)ctx->hpin[HSLOT_SEL];
+    const int32_t *ho = (const int32_t *)((const char *)ctx->hpin[HSLOT_SEL] + sizeof(long long) * rows);
+    sums.assign(hs, hs + rows);
     ord.resize(rows * K);
     for (int64_t i = 0; i < rows * K; ++i) ord[i] = ho[i];
+}
+
+int run_select_i32(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, int64_t n,
+                   const std::vector<int64_t> &ranks, std::vector<int64_t> &ord,
+                   std::vector<long long> &sums)
+{
+    int rc = select_launch(ctx, d_data, rows, ld, n, ranks, ctx->stream);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    select_collect(ctx, rows, (int)ranks.size(), ord, sums);
     return VX_OK;
 }
 
@@ -554,8 +602,9 @@ double acceptance_probability(const double *b)
 }
 
 // This shard's rejection count and moments of p_soft_no, left ON THE DEVICE (d_stats3).
-int launch_param_stats(vx_ctx *ctx, Job *j)
+int launch_param_stats(vx_ctx *ctx, Job *j, cudaStream_t st = nullptr)
 {
+    if (!st) st = ctx->stream;
     const int64_t n = j->shard_count, grid = (n + 255) / 256;
     unsigned long long *d_stop = nullptr;
     double *d_part = nullptr, *d_out = nullptr;
@@ -563,12 +612,12 @@ int launch_param_stats(vx_ctx *ctx, Job *j)
       rc_ = pool_get(ctx, SLOT_STATS_PART, sizeof(double) * 3 * grid, &p_); if (rc_) return rc_; d_part = (double *)p_;
       rc_ = pool_get(ctx, SLOT_STATS_MISC, 64, &p_); if (rc_) return rc_; d_stop = (unsigned long long *)p_; d_out = (double *)p_ + 4; }
     const unsigned long long hstop[2] = {0ull, (unsigned long long)(10 * j->cfg.n_samples)};
-    CK(cudaMemcpyAsync(d_stop, hstop, 16, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_stop, hstop, 16, cudaMemcpyHostToDevice, st));
     Bounds bd;
     memcpy(bd.b, j->cfg.bounds, sizeof bd.b);
-    vx_param_stats_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(bd, j->cfg.seed, j->shard_first, n, d_stop, d_part);
+    vx_param_stats_kernel<<<(unsigned)grid, 256, 0, st>>>(bd, j->cfg.seed, j->shard_first, n, d_stop, d_part);
     CKL();
-    vx_reduce_stats_kernel<<<1, 1024, 0, ctx->stream>>>(d_part, grid, d_out);
+    vx_reduce_stats_kernel<<<1, 1024, 0, st>>>(d_part, grid, d_out);
     CKL();
     j->d_stats3 = d_out;
     return VX_OK;
@@ -683,7 +732,7 @@ int vx_device_count(void)
     return n;
 }
 
-int vx_create(vx_ctx **out, int device)
+static int create_ctx(vx_ctx **out, int device, bool side_high_priority)
 {
     vx_ctx *ctx = nullptr;
     if (!out) return fail(nullptr, VX_ERR_ARG, "out is NULL");
@@ -699,7 +748,13 @@ int vx_create(vx_ctx **out, int device)
     c->trace = getenv("VX_TRACE") != nullptr;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // a grid sub-context runs its box's pilot on the side stream, which then outranks the main
+        // streams: the pilot is short and gates a long fold, other boxes' folds should not delay it
+        int lo_pri = 0, hi_pri = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+        e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_high_priority ? hi_pri : lo_pri);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int sm = 0;
@@ -713,6 +768,8 @@ int vx_create(vx_ctx **out, int device)
     delete c;
     return fail(nullptr, VX_ERR_CUDA, "vx_create: %s", cudaGetErrorString(e));
 }
+
+int vx_create(vx_ctx **out, int device) { return create_ctx(out, device, false); }
 
 void vx_destroy(vx_ctx *ctx)
 {
@@ -876,7 +933,11 @@ int vx_job_set_param_stats(vx_ctx *ctx, const double stats[4])
 
 int vx_job_is_direct(vx_ctx *ctx) { return (ctx && ctx->job && ctx->job->direct) ? 1 : 0; }
 
-int vx_job_pilot(vx_ctx *ctx)
+// The pilot in two halves.  pilot_launch queues everything up to the copy-back of the pilot's
+// order statistics (asynchronous; `on_side`: on the context's side stream, as the grid driver
+// wants it -- then nothing else is stepped beside it); pilot_complete, once that stream has been
+// synchronised, turns them into the window plan (host) and uploads it on the main stream.
+static int pilot_launch(vx_ctx *ctx, bool on_side)
 {
     if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
     Job *j = ctx->job;
@@ -884,17 +945,10 @@ int vx_job_pilot(vx_ctx *ctx)
     int rc = need_device(ctx);
     if (rc) return rc;
     j->piloted = true;
-    struct PilotTimer {
-        vx_ctx *c; Job *j;
-        PilotTimer(vx_ctx *c_, Job *j_) : c(c_), j(j_) { cudaEventRecord(j->evA, c->stream); }
-        ~PilotTimer() {
-            cudaEventRecord(j->evB, c->stream);
-            cudaEventSynchronize(j->evB);
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, j->evA, j->evB) == cudaSuccess) j->pilot_ms += ms;
-        }
-    } pilot_timer(ctx, j);
-    Phase ph_(ctx, "pilot (total)");
+    j->pilot_stage = 1;
+    cudaStream_t ps = on_side ? ctx->side : ctx->stream;
+    j->pilot_stream = ps;
+    CK(cudaEventRecord(j->evA, ps));
     if (j->cfg.mode == VX_MODE_EXPECTED) return run_expected(ctx);
 
     const int64_t n = j->cfg.n_samples, R = j->R;
@@ -906,7 +960,8 @@ int vx_job_pilot(vx_ctx *ctx)
 
     if (!j->direct && !ctx->use_pilot) {
         j->n_pilot = 0;
-        return plan_windows(ctx, false);
+        j->pilot_stage = 3;      // nothing in flight: plan from the certain bounds
+        return VX_OK;
     }
     // the default size balances the pilot's cost against the fold's, both PER RANK: with the range
     // sharded over `world` ranks (vx_run_bounds_comm) it is sized from n / world, a value every
@@ -921,7 +976,11 @@ int vx_job_pilot(vx_ctx *ctx)
         // (a) its first `side` samples are stepped NOW by a DUMP launch on the side stream: the
         //     pilot stepper is one serial T-day chain on < 1 CTA per SM, so the GPU is > 85 % idle
         //     until the windows exist; those rows are folded from their matrix afterwards
-        int64_t side = ctx->side_samples >= 0 ? ctx->side_samples : std::min<int64_t>(8 * np, (int64_t)1 << 18);
+        //     (default 2 x the pilot: measured on B200 at 1e6 samples, 0 / 32768 / 65536 / 131072 side
+        //     samples give 4.49 / 4.43 / 4.46 / 4.59 ms per job -- warps co-resident with the pilot's
+        //     slow its serial chain, so only a thin layer of extra work is free)
+        int64_t side = ctx->side_samples >= 0 ? ctx->side_samples : std::min<int64_t>(2 * np, (int64_t)1 << 18);
+        if (on_side) side = 0;
         side = std::min(side, hi - lo);
         if (side * 4 > hi - lo) side = (hi - lo >= 4096) ? (hi - lo) / 4 : 0;   // never more than a quarter of the shard
         side &= ~(int64_t)127;
@@ -942,47 +1001,75 @@ int vx_job_pilot(vx_ctx *ctx)
             if (rc) return rc;
             j->perm_first = lo; j->perm_count = hi - lo;
         }
-        CK(cudaEventRecord(ctx->side_done, ctx->side));
+        if (!on_side) CK(cudaEventRecord(ctx->side_done, ctx->side));
     }
     if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * R * np, &p_); if (rc_) return rc_; j->d_dump = (int32_t *)p_; }
-    { Phase ph2_(ctx, "  pilot stepper"); rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np); }
+    rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np, ps);
     if (rc) return rc;
 
-    std::vector<int64_t> ranks(4), ord;
-    std::vector<long long> sums;
+    j->pilot_ranks.assign(4, 0);
+    std::vector<int64_t> &ranks = j->pilot_ranks;
     if (j->direct) {
         double g;
         vx_host_quantile_index(n, j->cfg.q_lo, &ranks[0], &ranks[1], &g);
         vx_host_quantile_index(n, j->cfg.q_hi, &ranks[2], &ranks[3], &g);
-        rc = run_select_i32(ctx, j->d_dump, R, np, np, ranks, ord, sums);
-        if (rc) return rc;
+    } else {
+        // pilot order statistics bracketing each wanted quantile by +-k sigma of its rank
+        const double qs[2] = {j->cfg.q_lo, j->cfg.q_hi};
+        for (int q = 0; q < 2; ++q) {
+            const double sd = std::sqrt(std::max(qs[q] * (1 - qs[q]), 0.0));
+            const double delta = ctx->pilot_sigmas * sd * (1.0 / std::sqrt((double)np) + 1.0 / std::sqrt((double)n)) + 2.0 / (double)np;
+            const double ra = std::floor((double)(np - 1) * (qs[q] - delta)) - 1.0;
+            const double rb = std::ceil((double)(np - 1) * (qs[q] + delta)) + 1.0;
+            ranks[2 * q] = (int64_t)std::min(std::max(ra, 0.0), (double)(np - 1));
+            ranks[2 * q + 1] = (int64_t)std::min(std::max(rb, 0.0), (double)(np - 1));
+        }
+    }
+    rc = select_launch(ctx, j->d_dump, R, np, np, ranks, ps);
+    if (rc) return rc;
+    CK(cudaEventRecord(j->evB, ps));
+    if (on_side) CK(cudaEventRecord(ctx->side_done, ctx->side));
+    j->pilot_stage = 2;
+    return VX_OK;
+}
+
+static int pilot_complete(vx_ctx *ctx)
+{
+    Job *j = ctx->job;
+    if (j->pilot_stage == 1) return VX_OK;           // expected-value job: run_expected did everything
+    if (j->pilot_stage == 3) { j->pilot_stage = 0; return plan_windows(ctx, false); }
+    j->pilot_stage = 0;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, j->evA, j->evB) == cudaSuccess) j->pilot_ms += ms;
+    const int64_t n = j->cfg.n_samples, R = j->R, np = j->n_pilot;
+    std::vector<int64_t> ord;
+    std::vector<long long> sums;
+    select_collect(ctx, R, 4, ord, sums);
+    if (j->direct) {
         fill_from_counts(j, ord, sums, n);
         j->n_total = n;
         j->finished = true;
         return VX_OK;
     }
-    // pilot order statistics bracketing each wanted quantile by +-k sigma of its rank
-    const double qs[2] = {j->cfg.q_lo, j->cfg.q_hi};
-    for (int q = 0; q < 2; ++q) {
-        const double sd = std::sqrt(std::max(qs[q] * (1 - qs[q]), 0.0));
-        const double delta = ctx->pilot_sigmas * sd * (1.0 / std::sqrt((double)np) + 1.0 / std::sqrt((double)n)) + 2.0 / (double)np;
-        const double ra = std::floor((double)(np - 1) * (qs[q] - delta)) - 1.0;
-        const double rb = std::ceil((double)(np - 1) * (qs[q] + delta)) + 1.0;
-        ranks[2 * q] = (int64_t)std::min(std::max(ra, 0.0), (double)(np - 1));
-        ranks[2 * q + 1] = (int64_t)std::min(std::max(rb, 0.0), (double)(np - 1));
-    }
-    { Phase ph2_(ctx, "  pilot select"); rc = run_select_i32(ctx, j->d_dump, R, np, np, ranks, ord, sums); }
-    if (rc) return rc;
     j->pilot_stats = ord;
     // a bracket that ran off either end of the pilot sample is open on that side
+    const std::vector<int64_t> &ranks = j->pilot_ranks;
     for (int64_t r = 0; r < R; ++r)
         for (int q = 0; q < 2; ++q) {
             if (ranks[2 * q] == 0) j->pilot_stats[r * 4 + 2 * q] = 0;
             if (ranks[2 * q + 1] == np - 1) j->pilot_stats[r * 4 + 2 * q + 1] = j->vmax[series_of_row(j, r)];
         }
-    Phase ph3_(ctx, "  plan windows");
     return plan_windows(ctx, true);
+}
+
+int vx_job_pilot(vx_ctx *ctx)
+{
+    Phase ph_(ctx, "pilot (total)");
+    int rc = pilot_launch(ctx, false);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return pilot_complete(ctx);
 }
 
 int vx_job_acc(vx_ctx *ctx, void **device_ptr, int64_t *n_words)
@@ -1095,39 +1182,58 @@ static int accumulate_impl(vx_ctx *ctx, bool sync_end)
 
 int vx_job_accumulate(vx_ctx *ctx) { return accumulate_impl(ctx, true); }
 
-int vx_job_finalize(vx_ctx *ctx, vx_result *res)
+// Finalisation in two halves: finalize_launch queues the rank extraction and the copy-back into
+// pinned host memory (asynchronous, main stream); finalize_complete, after that stream has been
+// synchronised, resolves the targets on the host (or re-plans the windows: VX_REFINE).
+static int finalize_launch(vx_ctx *ctx)
 {
-    if (!ctx || !ctx->job || !res) return fail(ctx, VX_ERR_STATE, "no job");
+    if (!ctx || !ctx->job) return fail(ctx, VX_ERR_STATE, "no job");
     Job *j = ctx->job;
     int rc = need_device(ctx);
     if (rc) return rc;
     if (!j->piloted) return fail(ctx, VX_ERR_STATE, "vx_job_pilot must precede vx_job_finalize");
     if (!j->stats_set && !j->lstats_set && !j->stats_on_device)
         return fail(ctx, VX_ERR_STATE, "vx_job_param_stats (or vx_job_set_param_stats) must precede vx_job_finalize");
+    const int64_t R = j->R;
+    void *h = nullptr;
+    rc = hpin_get(ctx, HSLOT_FIN, sizeof(long long) * (R * 5 + ACC_HDR + 4), &h);
+    if (rc) return rc;
+    long long *hp = (long long *)h;           // [R*4] extract results | [R] sums | [ACC_HDR] header | [3] direct-job stats
+    if (!j->finished) {
+        const int64_t warps = 2 * R, grid = (warps * 32 + 255) / 256;
+        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R, j->cfg.q_lo, j->cfg.q_hi, j->bins64);
+        CKL();
+        CK(cudaMemcpyAsync(hp, j->d_res, sizeof(long long) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hp + R * 4, j->d_acc, sizeof(long long) * (ACC_HDR + R), cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (!j->stats_set && !j->lstats_set && j->stats_on_device) {
+        CK(cudaMemcpyAsync(hp + R * 5 + ACC_HDR, j->d_stats3, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+        j->stats_fetch_pending = true;
+    }
+    CK(cudaEventRecord(j->ev1, ctx->stream));
+    return VX_OK;
+}
+
+static int finalize_complete(vx_ctx *ctx, vx_result *res)
+{
+    Job *j = ctx->job;
+    int rc;
+    const int64_t R = j->R;
+    const long long *hp = (const long long *)ctx->hpin[HSLOT_FIN];
+    if (j->stats_fetch_pending) {
+        memcpy(j->lstats, hp + R * 5 + ACC_HDR, sizeof(double) * 3);
+        j->lstats[3] = (double)j->shard_count;
+        j->lstats_set = true;
+        j->stats_fetch_pending = false;
+    }
     if (!j->stats_set && j->direct) {       // a direct job without a statistics collective: local == global
-        if (!j->lstats_set && j->stats_on_device) {
-            CK(cudaMemcpyAsync(j->lstats, j->d_stats3, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            j->lstats[3] = (double)j->shard_count;
-            j->lstats_set = true;
-        }
         memcpy(j->gstats, j->lstats, sizeof j->gstats);
         j->stats_set = true;
         j->aborted = j->gstats[0] > 10.0 * (double)j->cfg.n_samples;
     }
-    Phase ph_(ctx, "finalize");
     if (!j->finished) {
-        const int64_t R = j->R;
-        unsigned long long hdr[ACC_HDR];
-        const int64_t warps = 2 * R, grid = (warps * 32 + 255) / 256;
-        vx_extract_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(j->d_acc, j->d_wins, j->d_tgt, j->d_res, (int)R, j->cfg.q_lo, j->cfg.q_hi, j->bins64);
-        CKL();
-        std::vector<long long> hres(R * 4);
-        std::vector<long long> sums(R);
-        CK(cudaMemcpyAsync(hres.data(), j->d_res, sizeof(long long) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(sums.data(), j->d_acc + ACC_HDR, sizeof(long long) * R, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(hdr, j->d_acc, sizeof hdr, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        const long long *hres = hp;
+        const unsigned long long *hdr = (const unsigned long long *)(hp + R * 4);
+        std::vector<long long> sums(hp + R * 4 + ACC_HDR, hp + R * 5 + ACC_HDR);
         if (j->fold_timing_pending) {
             float fms = 0.f;
             if (cudaEventElapsedTime(&fms, j->evA, j->evB) == cudaSuccess) j->fold_ms += fms;
@@ -1192,8 +1298,6 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
         fill_from_counts(j, ord, sums, n);
         j->finished = true;
     }
-    CK(cudaEventRecord(j->ev1, ctx->stream));
-    CK(cudaEventSynchronize(j->ev1));
     float ms = 0.f;
     cudaEventElapsedTime(&ms, j->ev0, j->ev1);
     res->device_ms = ms;
@@ -1206,6 +1310,16 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     res->side_samples = j->side_count;
     fill_result_scalars(ctx, res);
     return copy_results(ctx, res);
+}
+
+int vx_job_finalize(vx_ctx *ctx, vx_result *res)
+{
+    if (!res) return fail(ctx, VX_ERR_STATE, "no job");
+    Phase ph_(ctx, "finalize");
+    int rc = finalize_launch(ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return finalize_complete(ctx, res);
 }
 
 int vx_job_end(vx_ctx *ctx)
@@ -1277,6 +1391,134 @@ int vx_run_bounds(vx_ctx *ctx, const vx_config *cfg, vx_result *res)
     free_job(ctx);
     ctx->err = keep;
     return rc;
+}
+
+// ---- a batch of independent scenarios on one GPU (BASELINE configs[4]) -------------------------
+// Every box is a whole run_sampling job of its own (model.py:139-228 over its own parameter box).
+// Run one after the other each would pay its latency-bound pilot (~0.4 ms with the GPU > 85 %
+// idle) and three host round trips; here the boxes are software-pipelined over sub-contexts
+// (own streams, workspace and job state): while the boxes of one wave fold -- the GPU-saturating
+// part -- the next wave's pilots (stepper + select) run on high-priority streams in their shadow,
+// and the host only ever waits for work that was queued two waves ago.
+namespace {
+
+int grid_stage_a(vx_ctx *sub, const vx_config *cfg, vx_result *res, bool *skip)
+{
+    *skip = false;
+    int rc = job_begin_common(sub, cfg, 0, cfg->n_samples, nullptr);
+    if (rc) return rc;
+    Job *j = sub->job;
+    if (acceptance_probability(cfg->bounds) >= 0.25) {
+        rc = launch_param_stats(sub, j, sub->side);
+        if (rc) return rc;
+        j->stats_on_device = true;
+    } else {                                   // a mostly infeasible box: read the count first (rare)
+        double st[4];
+        rc = vx_job_param_stats(sub, st);
+        if (rc) return rc;
+        if (vx_job_set_param_stats(sub, st) == 1) {
+            res->device_ms = res->fold_ms = res->pilot_ms = res->merge_ms = 0; res->fold_launches = 0;
+            res->n_pilot = res->fold_samples = res->side_samples = 0;
+            fill_result_scalars(sub, res);
+            res->n_finished = 0;
+            *skip = true;
+            return VX_OK;
+        }
+    }
+    return pilot_launch(sub, true);
+}
+
+int grid_stage_b(vx_ctx *sub)
+{
+    vx_ctx *ctx = sub;
+    CK(cudaEventSynchronize(sub->side_done));
+    int rc = pilot_complete(sub);
+    if (rc) return rc;
+    rc = accumulate_impl(sub, false);
+    if (rc) return rc;
+    return finalize_launch(sub);
+}
+
+int grid_stage_c(vx_ctx *sub, vx_result *res)
+{
+    vx_ctx *ctx = sub;
+    CK(cudaStreamSynchronize(sub->stream));
+    int rc = finalize_complete(sub, res);
+    for (int it = 0; rc == VX_REFINE && it < 64; ++it) {      // rare: a rank fell outside its window
+        rc = accumulate_impl(sub, false);
+        if (rc) return rc;
+        rc = vx_job_finalize(sub, res);
+    }
+    return rc == VX_REFINE ? fail(sub, VX_ERR_STATE, "window refinement did not converge") : rc;
+}
+
+} // namespace
+
+int vx_run_grid(vx_ctx *ctx, const vx_config *cfgs, int32_t n_boxes, vx_result *results, int32_t wave)
+{
+    if (!ctx || !cfgs || !results || n_boxes < 0) return fail(ctx, VX_ERR_ARG, "bad grid arguments");
+    if (ctx->job) return fail(ctx, VX_ERR_STATE, "vx_run_grid while a job is open");
+    int rc = need_device(ctx);
+    if (rc) return rc;
+    const int G = wave > 0 ? std::min(wave, 64) : 8;
+    while ((int)ctx->subs.size() < 2 * G) {
+        vx_ctx *sub = nullptr;
+        rc = create_ctx(&sub, ctx->device, true);
+        if (rc) return fail(ctx, rc, "vx_run_grid: %s", g_create_error.c_str());
+        ctx->subs.push_back(sub);
+    }
+    for (vx_ctx *sub : ctx->subs) {
+        sub->max_bins = ctx->max_bins; sub->chunk_samples = ctx->chunk_samples; sub->pilot_sigmas = ctx->pilot_sigmas;
+        sub->use_pilot = ctx->use_pilot; sub->sort_samples = ctx->sort_samples; sub->exact_poisson = ctx->exact_poisson;
+    }
+    const int n_waves = (n_boxes + G - 1) / G;
+    std::vector<char> skip(n_boxes, 0);
+    auto sub_of = [&](int b) { return ctx->subs[((b / G) & 1) * G + (b % G)]; };
+    auto fail_from = [&](vx_ctx *sub, int code) {
+        ctx->err = sub->err;
+        for (vx_ctx *x : ctx->subs) { cudaStreamSynchronize(x->stream); cudaStreamSynchronize(x->side); free_job(x); }
+        return code;
+    };
+    auto stage_a = [&](int w) {
+        for (int b = w * G; b < std::min(n_boxes, (w + 1) * G); ++b) {
+            bool sk = false;
+            const int r = grid_stage_a(sub_of(b), &cfgs[b], &results[b], &sk);
+            if (r) return fail_from(sub_of(b), r);
+            skip[b] = sk;
+            if (sk) free_job(sub_of(b));
+        }
+        return (int)VX_OK;
+    };
+    auto stage_b = [&](int w) {
+        for (int b = w * G; b < std::min(n_boxes, (w + 1) * G); ++b) {
+            if (skip[b]) continue;
+            const int r = grid_stage_b(sub_of(b));
+            if (r) return fail_from(sub_of(b), r);
+        }
+        return (int)VX_OK;
+    };
+    auto stage_c = [&](int w) {
+        for (int b = w * G; b < std::min(n_boxes, (w + 1) * G); ++b) {
+            if (skip[b]) continue;
+            vx_ctx *sub = sub_of(b);
+            const int r = grid_stage_c(sub, &results[b]);
+            if (r) return fail_from(sub, r);
+            free_job(sub);
+        }
+        return (int)VX_OK;
+    };
+    const int64_t l0 = [&] { int64_t t = 0; for (vx_ctx *x : ctx->subs) t += x->launches; return t; }();
+    if (n_waves > 0 && (rc = stage_a(0))) return rc;
+    for (int w = 0; w < n_waves; ++w) {
+        if ((rc = stage_b(w))) return rc;                        // wave w: pilots done -> folds queued
+        if (w >= 1 && (rc = stage_c(w - 1))) return rc;          // wave w-1: results (its sub-contexts become free)
+        if (w + 1 < n_waves && (rc = stage_a(w + 1))) return rc; // wave w+1: pilots, in the shadow of wave w's folds
+    }
+    if (n_waves > 0 && (rc = stage_c(n_waves - 1))) return rc;
+    int64_t l1 = 0;
+    for (vx_ctx *x : ctx->subs) l1 += x->launches;
+    ctx->launches += l1 - l0;
+    return VX_OK;
 }
 
 // ---- multi-GPU: one rank of a job sharded over the ranks of the context's communicator -------

@@ -199,56 +199,38 @@ def run_model(
     return ret
 
 
-def run_model_grid(boxes, CI, n_rep, N, date_range, *, seeds=None, device=None, workers=2,
-                   mode="stochastic", direct_max=0, pilot_samples=0):
+def run_model_grid(boxes, CI, n_rep, N, date_range, *, seeds=None, device=None, workers=None,
+                   mode="stochastic", direct_max=0, pilot_samples=0, wave=0):
     """Batched multi-scenario form of run_model (BASELINE.json configs[4]).
 
     `boxes` is a sequence of (p_pro_bounds, p_anti_bounds, pressure_bounds, tau_bounds,
     nv_0_bounds, nv_max_bounds) in run_model's user units; returns a list of run_model triples in
-    the same order.  Scenarios are independent, so they are issued from `workers` host threads,
-    each with its own libvaxmc context on the same GPU: while one scenario's latency-bound pilot
-    runs (the GPU is ~90 % idle then), the other's fold keeps the SMs busy.  Under torchrun the
-    caller partitions the boxes over ranks (no collective is needed)."""
-    from concurrent.futures import ThreadPoolExecutor
-
+    the same order, each identical to what run_model(box, ..., seed=seeds[i]) returns.  The boxes
+    go to the library in ONE call (vx_run_grid): it pipelines them over sub-contexts so that the
+    latency-bound pilots of the next boxes run in the shadow of the current boxes' folds and the
+    host never waits on a kernel it has just queued.  Under torchrun the caller partitions the
+    boxes over ranks (no collective is needed).  `workers` is accepted for compatibility with the
+    first version (host threads) and ignored."""
     daily, weekly = _dates(date_range["start_date"], date_range["end_date"])
     T = len(daily)
     ci_frac = CI / 100
     vx_mode = nat.MODE_EXPECTED if mode == "expected" else nat.MODE_STOCHASTIC
-    dev = _device_index(device)
     boxes = list(boxes)
     if seeds is None:
         seeds = [_next_seed(None)[0] for _ in boxes]
-    workers = max(1, min(int(workers), len(boxes) or 1))
-    ctxs = [nat.default_context(dev)] + [nat.Context(dev) for _ in range(workers - 1)]
-
-    def one(i, ctx):
-        b = boxes[i]
+    cfgs = []
+    for b, sd in zip(boxes, seeds):
         bounds = _bounds12(np.array(b[0]) / 100, np.array(b[1]) / 100, np.array(b[2]), np.array(b[3]),
                            np.array(b[4]) / 100, np.array(b[5]) / 100)
-        cfg = nat.make_config(bounds, N, T, n_rep, seeds[i], (1 - ci_frac) / 2.0, (1 + ci_frac) / 2.0,
-                              mode=vx_mode, direct_max=direct_max, pilot_samples=pilot_samples)
-        out = ctx.run_bounds(cfg)
+        cfgs.append(nat.make_config(bounds, N, T, n_rep, sd, (1 - ci_frac) / 2.0, (1 + ci_frac) / 2.0,
+                                    mode=vx_mode, direct_max=direct_max, pilot_samples=pilot_samples))
+    outs = nat.default_context(_device_index(device)).run_grid(cfgs, wave=wave) if cfgs else []
+    res = []
+    for out in outs:
         if out.c.aborted:
-            return None, MSG_ERR_BOUNDS, "Agnosticts: "
-        return _pack(out, daily, weekly), "", _agnostics_message(out.c.soft_no_mean, out.c.soft_no_std)
-
-    def lane(k):
-        return [(i, one(i, ctxs[k])) for i in range(k, len(boxes), workers)]
-
-    try:
-        if workers == 1:
-            parts = [lane(0)]
+            res.append((None, MSG_ERR_BOUNDS, "Agnosticts: "))
         else:
-            with ThreadPoolExecutor(max_workers=workers) as ex:
-                parts = list(ex.map(lane, range(workers)))
-    finally:
-        for c in ctxs[1:]:
-            c.close()
-    res = [None] * len(boxes)
-    for part in parts:
-        for i, r in part:
-            res[i] = r
+            res.append((_pack(out, daily, weekly), "", _agnostics_message(out.c.soft_no_mean, out.c.soft_no_std)))
     return res
 
 

@@ -122,7 +122,7 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * (granularity of the max_running_time check, default 2^20), "exact_poisson" (1: validation
  * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; ~11x slower),
  * "side_samples" (samples stepped on a side stream while the pilot runs and folded from their
- * matrix; -1 = default 8 x pilot, 0 = none; same integers either way).                       */
+ * matrix; -1 = default 2 x pilot, 0 = none; same integers either way).                       */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
  * vx_trim returns it to the driver. */
@@ -147,6 +147,15 @@ int vx_comm_destroy(vx_ctx *ctx);
 int vx_comm_info(vx_ctx *ctx, int *rank, int *world, int *nccl_version);
 int vx_run_bounds_comm(vx_ctx *ctx, const vx_config *cfg, vx_result *res);
 void vx_host_shard_range(int64_t n, int rank, int world, int64_t *first, int64_t *count);
+
+/* ---- a batch of independent scenarios on one GPU (BASELINE.json configs[4]) -------------------
+ * cfgs[0..n_boxes): one whole job each (own bounds / seed / sizes), results[b] with caller-allocated
+ * buffers like vx_run_bounds.  Equivalent to n_boxes calls of vx_run_bounds (same bytes out), but
+ * pipelined: the boxes' latency-bound pilots run on high-priority streams in the shadow of other
+ * boxes' folds, and the host never waits for a kernel it has just queued.  `wave` = boxes in
+ * flight per pipeline stage (0: default 8; 2 x wave sub-contexts are kept by ctx until vx_trim).
+ * Under torchrun the caller partitions the boxes over ranks; no collective is involved.         */
+int vx_run_grid(vx_ctx *ctx, const vx_config *cfgs, int32_t n_boxes, vx_result *results, int32_t wave);
 
 /* Same reduction over EXPLICIT parameter tuples, params = host [n][6] row-major in the
  * reference's tuple order (model.py:296-300).  cfg->bounds is ignored, cfg->n_samples = n.

@@ -613,24 +613,32 @@ def test_wide_5y_streamed_properties(vax, ctx):
 
 
 def test_run_model_grid_equals_sequential_run_model(vax):
-    """configs[4] entry point: scenarios issued from 2 threads/contexts == one by one."""
+    """configs[4] entry point: the boxes pipelined by vx_run_grid (several waves, a ragged last
+    wave, an infeasible and an almost infeasible box in the middle) == run_model one by one."""
     import bench
 
-    boxes = bench.grid_boxes(6, seed=5)
+    boxes = bench.grid_boxes(10, seed=5)
     args = [(b["pro"], b["anti"], b["pressure"], b["tau"], b["nv0"], b["nvmax"]) for b in boxes]
-    args.append(([70, 90], [50, 60], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10]))      # infeasible box
+    args.insert(4, ([70, 90], [50, 60], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10]))      # infeasible box
+    args.insert(8, ([60, 99], [38, 99], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10]))      # aborts on the rejection count
     seeds = [100 + i for i in range(len(args))]
-    grid = vax.run_model_grid(args, 99, 150_000, 50000, USA_DATES, seeds=seeds, workers=2)
-    assert len(grid) == len(args)
-    for a, s_, g in zip(args, seeds, grid):
-        res, err, msg = vax.run_model(*a, 99, 150_000, 50000, USA_DATES, seed=s_)
-        assert (err, msg) == (g[1], g[2])
-        if res is None:
-            assert g[0] is None and err == ro.ERR_BOUNDS
-            continue
-        for k in SERIES:
-            for f in ("mean", "lower", "upper"):
-                assert np.array_equal(res[k][f], g[0][k][f]), (k, f)
+    for n_rep, wave in ((150_000, 3), (150_000, 0), (2_000, 5)):                         # streamed jobs, direct jobs
+        grid = vax.run_model_grid(args, 99, n_rep, 50000, USA_DATES, seeds=seeds, wave=wave)
+        assert len(grid) == len(args)
+        n_none = 0
+        for a, s_, g in zip(args, seeds, grid):
+            res, err, msg = vax.run_model(*a, 99, n_rep, 50000, USA_DATES, seed=s_)
+            assert (err, msg) == (g[1], g[2])
+            if res is None:
+                assert g[0] is None and err == ro.ERR_BOUNDS
+                n_none += 1
+                continue
+            assert g[0]["number_finished_samples"] == n_rep
+            for k in SERIES:
+                for f in ("mean", "lower", "upper"):
+                    assert np.array_equal(res[k][f], g[0][k][f]), (k, f)
+        assert n_none == 2
+    assert vax.run_model_grid([], 99, 1000, 50000, USA_DATES) == []
 
 
 def test_integration_md_stub_runs_and_matches(vax):
