@@ -248,7 +248,7 @@ def run_reference_arm(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": ("the reference is pure Python and cannot travel to the GPU box (no /root/reference "
-                 "there); this arm times the C restatement of its algorithm, which is ~15x faster "
+                 "there); this arm times the C restatement of its algorithm, which is ~25x faster "
                  "per core than the Python original (SURVEY.md 6: 3.5-4.0e4 sample-weeks/s/core)"),
     }
     print(json.dumps(line))
