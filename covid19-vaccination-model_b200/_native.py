@@ -215,7 +215,13 @@ def make_config(bounds, N, T, n_samples, seed, q_lo, q_hi, mode=MODE_STOCHASTIC,
     cfg.q_hi = float(q_hi)
     cfg.direct_max = int(direct_max)
     cfg.pilot_samples = int(pilot_samples)
-    cfg.max_running_time = float(max_running_time) if max_running_time else 0.0
+    # vx_config: <= 0 means "no limit".  The reference checks `elapsed > max_running_time` after every
+    # sample (model.py:187-189), so a budget of 0 is a REAL limit there (one sample, then stop): it
+    # is passed on as the smallest positive budget, which stops the job after its first chunk.
+    if max_running_time is None:
+        cfg.max_running_time = 0.0
+    else:
+        cfg.max_running_time = max(float(max_running_time), 1e-12)
     return cfg
 
 

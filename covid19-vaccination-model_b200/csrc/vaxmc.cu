@@ -681,9 +681,10 @@ int run_expected(vx_ctx *ctx)
     vx_host_quantile_index(n, j->cfg.q_hi, &p1, &n1, &g1);
     const int64_t hr[4] = {p0, n0, p1, n1};
     int64_t *d_ranks = nullptr; double *d_out = nullptr, *d_sums = nullptr;
-    CK(cudaMalloc(&d_ranks, sizeof hr));
-    CK(cudaMalloc(&d_out, sizeof(double) * RE * 4));
-    CK(cudaMalloc(&d_sums, sizeof(double) * RE));
+    { void *p_ = nullptr; int rc_;       // workspace slots: nothing to free on an error path
+      rc_ = pool_get(ctx, SLOT_TMP_A, sizeof hr, &p_); if (rc_) return rc_; d_ranks = (int64_t *)p_;
+      rc_ = pool_get(ctx, SLOT_TMP_B, sizeof(double) * RE * 4, &p_); if (rc_) return rc_; d_out = (double *)p_;
+      rc_ = pool_get(ctx, SLOT_TMP_C, sizeof(double) * RE, &p_); if (rc_) return rc_; d_sums = (double *)p_; }
     CK(cudaMemcpyAsync(d_ranks, hr, sizeof hr, cudaMemcpyHostToDevice, ctx->stream));
     vx_select_kernel<double><<<(unsigned)RE, SEL_THREADS, 0, ctx->stream>>>(j->d_exp, n, n, d_ranks, 4, d_out, d_sums);
     CKL();
@@ -691,7 +692,6 @@ int run_expected(vx_ctx *ctx)
     CK(cudaMemcpyAsync(ho.data(), d_out, sizeof(double) * RE * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(hs.data(), d_sums, sizeof(double) * RE, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_ranks); cudaFree(d_out); cudaFree(d_sums);
     alloc_results(j);
     const int len[4] = {j->T, j->W, j->T, j->T};
     for (int s = 0; s < 4; ++s)
@@ -1133,7 +1133,11 @@ static int accumulate_impl(vx_ctx *ctx, bool sync_end)
         done += j->side_count;
     }
     int64_t stepped = 0;
+    auto out_of_time = [&]() {       // model.py:187-189, at chunk granularity; something is always folded first
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - j->t_begin).count() > j->cfg.max_running_time;
+    };
     while (done < todo) {
+        if (timed && done > 0 && out_of_time()) break;
         const int64_t cnt = std::min(chunk, todo - done);
         SimArgs a = make_args(j, j->shard_first + done, cnt,
                               j->d_params ? j->d_params + 6 * (j->shard_first + done) : nullptr);
@@ -1156,11 +1160,7 @@ static int accumulate_impl(vx_ctx *ctx, bool sync_end)
         j->fold_launches++;
         done += cnt;
         stepped += cnt;
-        if (timed) {
-            CK(cudaStreamSynchronize(ctx->stream));
-            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - j->t_begin).count();
-            if (el > j->cfg.max_running_time) break;   // model.py:187-189
-        }
+        if (timed) CK(cudaStreamSynchronize(ctx->stream));
     }
     if (first_pass) { j->shard_done = done; j->fold_samples = stepped; }
     j->n_passes++;
@@ -1621,8 +1621,9 @@ int vx_sample_params(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t c
     if (count < 0 || !params_out) return fail(ctx, VX_ERR_ARG, "bad output");
     if (count == 0) return VX_OK;
     double *d_p = nullptr, *d_s = nullptr;
-    CK(cudaMalloc(&d_p, sizeof(double) * 6 * count));
-    if (p_soft_no_out) CK(cudaMalloc(&d_s, sizeof(double) * count));
+    { void *p_ = nullptr; int rc_;
+      rc_ = pool_get(ctx, SLOT_TMP_A, sizeof(double) * 6 * count, &p_); if (rc_) return rc_; d_p = (double *)p_;
+      if (p_soft_no_out) { rc_ = pool_get(ctx, SLOT_TMP_B, sizeof(double) * count, &p_); if (rc_) return rc_; d_s = (double *)p_; } }
     Bounds bd;
     memcpy(bd.b, cfg->bounds, sizeof bd.b);
     vx_sample_params_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(bd, cfg->seed, first, count, d_p, d_s);
@@ -1630,7 +1631,6 @@ int vx_sample_params(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t c
     CK(cudaMemcpyAsync(params_out, d_p, sizeof(double) * 6 * count, cudaMemcpyDeviceToHost, ctx->stream));
     if (p_soft_no_out) CK(cudaMemcpyAsync(p_soft_no_out, d_s, sizeof(double) * count, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_p); cudaFree(d_s);
     return VX_OK;
 }
 
@@ -1645,15 +1645,12 @@ int vx_dump_counts(vx_ctx *ctx, const vx_config *cfg, int64_t first, int64_t cou
     Job tmp;
     tmp.cfg = *cfg; tmp.T = cfg->T; tmp.W = (cfg->T + 6) / 7; tmp.R = vx_host_rows(cfg->T);
     int32_t *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(int32_t) * tmp.R * count));
+    { void *p_ = nullptr; rc = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * tmp.R * count, &p_); if (rc) return rc; d = (int32_t *)p_; }
     rc = launch_dump(ctx, &tmp, first, count, nullptr, d, count);
-    if (rc == VX_OK) {
-        cudaError_t e = cudaMemcpyAsync(counts_out, d, sizeof(int32_t) * tmp.R * count, cudaMemcpyDeviceToHost, ctx->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = fail(ctx, VX_ERR_CUDA, "vx_dump_counts: %s", cudaGetErrorString(e));
-    }
-    cudaFree(d);
-    return rc;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(counts_out, d, sizeof(int32_t) * tmp.R * count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return VX_OK;
 }
 
 int vx_expected_series(vx_ctx *ctx, const vx_config *cfg, const double *params, int64_t n,
@@ -1671,8 +1668,9 @@ int vx_expected_series(vx_ctx *ctx, const vx_config *cfg, const double *params, 
     tmp.cfg = c; tmp.T = c.T; tmp.W = (c.T + 6) / 7;
     const int64_t RE = 4 * (int64_t)c.T + tmp.W, T = c.T;
     double *d_p = nullptr, *d_o = nullptr;
-    CK(cudaMalloc(&d_p, sizeof(double) * 6 * n));
-    CK(cudaMalloc(&d_o, sizeof(double) * RE * n));
+    { void *p_ = nullptr; int rc_;
+      rc_ = pool_get(ctx, SLOT_PARAMS, sizeof(double) * 6 * n, &p_); if (rc_) return rc_; d_p = (double *)p_;
+      rc_ = pool_get(ctx, SLOT_EXP, sizeof(double) * RE * n, &p_); if (rc_) return rc_; d_o = (double *)p_; }
     CK(cudaMemcpyAsync(d_p, params, sizeof(double) * 6 * n, cudaMemcpyHostToDevice, ctx->stream));
     SimArgs a = make_args(&tmp, 0, n, d_p);
     vx_expected_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a, d_o, n);
@@ -1680,7 +1678,6 @@ int vx_expected_series(vx_ctx *ctx, const vx_config *cfg, const double *params, 
     std::vector<double> h(4 * T * n);
     CK(cudaMemcpyAsync(h.data(), d_o, sizeof(double) * 4 * T * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_p); cudaFree(d_o);
     for (int s = 0; s < 4; ++s)
         for (int64_t t = 0; t < T; ++t)
             for (int64_t i = 0; i < n; ++i)
@@ -1694,12 +1691,11 @@ int vx_test_philox(vx_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], ui
     int rc = need_device(ctx);
     if (rc) return rc;
     uint32_t *d = nullptr;
-    CK(cudaMalloc(&d, 16));
+    { void *p_ = nullptr; rc = pool_get(ctx, SLOT_TMP_A, 16, &p_); if (rc) return rc; d = (uint32_t *)p_; }
     vx_test_philox_kernel<<<1, 1, 0, ctx->stream>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_uint2(key[0], key[1]), d);
     CKL();
     CK(cudaMemcpyAsync(out, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d);
     return VX_OK;
 }
 
@@ -1709,12 +1705,11 @@ int vx_test_poisson(vx_ctx *ctx, double lam, int64_t n, uint64_t seed, int32_t *
     if (rc) return rc;
     if (n < 1 || !out_host) return fail(ctx, VX_ERR_ARG, "bad argument");
     int32_t *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(int32_t) * n));
+    { void *p_ = nullptr; rc = pool_get(ctx, SLOT_TMP_A, sizeof(int32_t) * n, &p_); if (rc) return rc; d = (int32_t *)p_; }
     vx_test_poisson_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((float)lam, n, seed, d, (int)ctx->exact_poisson);
     CKL();
     CK(cudaMemcpyAsync(out_host, d, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d);
     return VX_OK;
 }
 
@@ -1724,13 +1719,12 @@ int vx_test_normal(vx_ctx *ctx, int64_t n, uint64_t seed, float *out_host)
     if (rc) return rc;
     if (n < 1 || !out_host) return fail(ctx, VX_ERR_ARG, "bad argument");
     float *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(float) * n));
+    { void *p_ = nullptr; rc = pool_get(ctx, SLOT_TMP_A, sizeof(float) * n, &p_); if (rc) return rc; d = (float *)p_; }
     const int64_t pairs = (n + 1) / 2;
     vx_test_normal_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(n, seed, d);
     CKL();
     CK(cudaMemcpyAsync(out_host, d, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d);
     return VX_OK;
 }
 
@@ -1744,12 +1738,11 @@ int vx_test_select(vx_ctx *ctx, const int32_t *data, int64_t rows, int64_t n, co
     for (int k = 0; k < n_ranks; ++k)
         if (ranks[k] < 0 || ranks[k] >= n) return fail(ctx, VX_ERR_ARG, "rank out of range");
     int32_t *d = nullptr;
-    CK(cudaMalloc(&d, sizeof(int32_t) * rows * n));
+    { void *p_ = nullptr; rc = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * rows * n, &p_); if (rc) return rc; d = (int32_t *)p_; }
     CK(cudaMemcpyAsync(d, data, sizeof(int32_t) * rows * n, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int64_t> rk(ranks, ranks + n_ranks), ord;
     std::vector<long long> sm;
     rc = run_select_i32(ctx, d, rows, n, n, rk, ord, sm);
-    cudaFree(d);
     if (rc) return rc;
     for (int64_t i = 0; i < rows * n_ranks; ++i) out[i] = (int32_t)ord[i];
     if (sums) for (int64_t i = 0; i < rows; ++i) sums[i] = sm[i];

@@ -78,7 +78,11 @@ typedef struct vx_config {
     int64_t direct_max;      /* n_samples <= this: materialise + exact radix select;
                                 above: pilot + streaming fold.  0 = library default          */
     int64_t pilot_samples;   /* size of the pilot used to place the windows. 0 = default     */
-    double max_running_time; /* seconds, <= 0: none (model.py:187-189)                       */
+    double max_running_time; /* seconds, <= 0: none (model.py:187-189).  Checked between chunks of
+                                "chunk_samples" of the streaming fold (the first chunk always runs,
+                                as the reference's first sample does); a direct job (n_samples <=
+                                direct_max, < 2 ms of GPU time) and an expected-value job are ONE
+                                chunk and therefore always complete.                             */
 } vx_config;
 
 typedef struct vx_result {

@@ -573,6 +573,19 @@ def test_max_running_time_partial_results(vax, ctx):
     assert err == (f"ERROR: Maximum computation time of 0.0001s exceeded. Only {k} of the desired "
                    f"3000000 Monte Carlo runs were performed.")
     assert np.isfinite(res[SERIES[0]]["mean"]).all()
+    # a budget of 0 is a real limit in the reference (one sample, then stop): here one chunk
+    ctx.set_option("chunk_samples", 4096)
+    try:
+        res0, err0, _ = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95,
+                                      3_000_000, 50000, USA_DATES, max_running_time=0, seed=1,
+                                      direct_max=1, pilot_samples=4096)
+    finally:
+        ctx.set_option("chunk_samples", 1 << 20)
+    assert res0["number_finished_samples"] == 4096 and "Maximum computation time of 0s exceeded" in err0
+    # a direct job is one chunk: it always completes, and then there is no error (model.py:364-366)
+    res1, err1, _ = vax.run_model([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10], 95,
+                                  1000, 50000, USA_DATES, max_running_time=0, seed=1)
+    assert res1["number_finished_samples"] == 1000 and err1 == ""
 
 
 # ------------------------------------------------------- full BASELINE sizes: properties
