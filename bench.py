@@ -255,61 +255,68 @@ def run_reference_arm(args):
     return 0
 
 
-def run_grid(args, vax, ctx, rank, world, local_rank, dist):
-    """configs[4]: independent scenarios -> partition BOXES over ranks, no data-path collective."""
-    import numpy as np
+def time_grid(vax, ctx, rank, world, local_rank, dist, n_boxes, samples, ci, wave, warmup, steps):
+    """configs[4]: independent scenarios -> partition BOXES over ranks, no data-path collective.
+    Host wall clock around the whole grid incl. the copy-back of every box's bands, max over ranks."""
     import torch
 
-    nat = vax._native
-    ci = args.ci if args.ci is not None else 99.0
-    q_lo, q_hi = (1 - ci / 100) / 2.0, (1 + ci / 100) / 2.0
-    boxes = grid_boxes(args.boxes)
-    mine = list(range(rank, args.boxes, world))
-
+    boxes = grid_boxes(n_boxes)
+    mine = list(range(rank, n_boxes, world))
     box_args = [(boxes[b]["pro"], boxes[b]["anti"], boxes[b]["pressure"], boxes[b]["tau"], boxes[b]["nv0"],
                  boxes[b]["nvmax"]) for b in mine]
 
     def one_pass(seed0):
         # the product's batched entry point: ONE library call per rank (vx_run_grid) pipelines the
         # boxes -- next boxes' pilots in the shadow of the current boxes' folds
-        res = vax.run_model_grid(box_args, ci, args.samples, N_POP, DATES, seeds=[seed0 + b for b in mine],
-                                 device=local_rank, wave=args.grid_wave)
+        res = vax.run_model_grid(box_args, ci, samples, N_POP, DATES, seeds=[seed0 + b for b in mine],
+                                 device=local_rank, wave=wave)
         checksum = 0.0
         for r, err, msg in res:
             assert err == ""
             checksum += float(r["people_vaccinated_per_hundred"]["mean"][-1])
-        return checksum, 0.0
+        return checksum
 
-    for i in range(args.warmup):
+    for i in range(warmup):
         one_pass(10_000 * i)
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     l0 = ctx.launch_count
-    t0 = time.perf_counter()
-    tot_ms = 0.0
-    for i in range(args.steps):
-        cs, ms = one_pass(1_000_000 + 10_000 * i)
-        tot_ms += ms
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    t = torch.tensor([wall, tot_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    per_step = []
+    for i in range(steps):
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        one_pass(1_000_000 + 10_000 * i)
+        per_step.append(time.perf_counter() - t0)
+    t = torch.tensor(per_step, dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    per_step = [float(x) for x in t.tolist()]
+    units = n_boxes * samples * T_DAYS / 7.0
+    return {"workload": "batched multi-scenario grid (BASELINE configs[4]): %d bound boxes x %g samples, CI=%g, "
+                        "boxes partitioned over ranks, one vx_run_grid call per rank" % (n_boxes, samples, ci),
+            "boxes": n_boxes, "samples_per_box": samples, "days": T_DAYS, "N": N_POP,
+            "generator": "bench.grid_boxes(seed=20261019)",
+            "sample_weeks_per_s": units * steps / sum(per_step), "ms_per_step": 1e3 * sum(per_step) / steps,
+            "step_ms": [1e3 * x for x in per_step],
+            "step_spread": (max(per_step) - min(per_step)) / (sum(per_step) / steps) if steps > 1 else 0.0,
+            "steps": steps, "warmup": warmup, "grid_wave": wave, "gpu_launches": ctx.launch_count - l0,
+            "timing": "host wall clock around the whole grid incl. D2H of every box's bands (max over ranks)"}
+
+
+def run_grid(args, vax, ctx, rank, world, local_rank, dist):
+    ci = args.ci if args.ci is not None else 99.0
+    g = time_grid(vax, ctx, rank, world, local_rank, dist, args.boxes, args.samples, ci, args.grid_wave,
+                  args.warmup, args.steps)
     if rank == 0:
-        units = args.boxes * args.samples * T_DAYS / 7.0 * args.steps
         print(json.dumps({
-            "metric": "MC sample-weeks/sec", "value": units / float(t[0].item()), "unit": "sample-weeks/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * float(t[0].item()) / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "int32 state / fp32 sampler / fp64 arrivals",
-            "data": "synthetic",
-            "config": {"workload": "batched multi-scenario grid (BASELINE configs[4]): %d bound boxes x %g samples, "
-                                   "CI=%g, boxes partitioned over ranks" % (args.boxes, args.samples, ci),
-                       "boxes": args.boxes, "samples_per_box": args.samples, "days": T_DAYS, "N": N_POP,
-                       "generator": "bench.grid_boxes(seed=20261019)"},
-            "grid_wave": args.grid_wave, "gpu_launches": ctx.launch_count - l0,
-            "timing": "host wall clock around the whole grid incl. D2H of every box's bands (max over ranks)"}))
+            "metric": "MC sample-weeks/sec", "value": g["sample_weeks_per_s"], "unit": "sample-weeks/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": g["ms_per_step"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 state / fp32 sampler / fp64 arrivals", "data": "synthetic",
+            "config": {k: g[k] for k in ("workload", "boxes", "samples_per_box", "days", "N", "generator")},
+            "grid": g, "gpu_launches": g["gpu_launches"]}))
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -332,6 +339,8 @@ def main():
                     help="force the materialise + radix-select path (HBM-bound passes) instead of the streaming fold")
     ap.add_argument("--target-samples", type=int, default=1_000_000_000,
                     help="global samples of the target_1e9 block (BASELINE configs[2]); 0 skips it")
+    ap.add_argument("--grid-boxes", type=int, default=1024,
+                    help="boxes of the grid_1024 block (BASELINE configs[4], 1e6 samples each, CI=99); 0 skips it")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -505,6 +514,11 @@ def main():
                   "warmup_calls": 1, "api": "run_model(..., n_rep=%d, CI=95), host wall clock, max over ranks"
                                             % args.target_samples}
 
+    # ---------------- BASELINE configs[4] as a secondary block: 1024 boxes x 1e6 samples, CI=99
+    grid = None
+    if args.grid_boxes > 0 and args.workload == "usa":
+        grid = time_grid(vax, ctx, rank, world, local_rank, dist, args.grid_boxes, 1_000_000, 99.0, args.grid_wave, 1, 2)
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -569,7 +583,7 @@ def main():
         "config": workload_config(args, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu,
-        "bitexact": bitexact, "target_1e9": target,
+        "bitexact": bitexact, "target_1e9": target, "grid_1024": grid,
         "wall_s_timed_region": wall_s,
         "passes_per_step": statistics.mean(passes) if passes else 0,
         "breakdown_ms_per_step": {"pilot": sum(pilot_ms) / args.steps, "fold": sum(fold_ms) / args.steps,

@@ -15,6 +15,7 @@ import importlib
 import json
 import os
 import sys
+import time
 
 import numpy as np
 import torch
@@ -42,10 +43,17 @@ def main():
          400_000, dict(start_date="2020-12-15", end_date="2025-12-14")),
         ("usa n=1000 (direct job, no collective)", ([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10]),
          95, 1000, dict(start_date="2020-12-15", end_date="2022-07-1")),
+        # the Dash app's maximum population (app.py:157-166): deliveries/stock spread over millions of doses,
+        # the widest windows and the largest slab the all-reduce ever carries
+        ("usa N=1e6 population n=1e6 CI=95", ([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10]),
+         95, 1_000_000, dict(start_date="2020-12-15", end_date="2022-07-1"), 1_000_000),
     ]
     ok_all = True
-    for name, b, ci, n, dates in scen:
-        res, err, msg = vax.run_model(*b, ci, n, 50000, dates, seed=20261020)     # sharded over `world` ranks
+    for name, b, ci, n, dates, *rest in scen:
+        N = rest[0] if rest else 50000
+        t0 = time.perf_counter()
+        res, err, msg = vax.run_model(*b, ci, n, N, dates, seed=20261020)         # sharded over `world` ranks
+        wall_ms = 1e3 * (time.perf_counter() - t0)
         digest = float(sum(res[k][f].sum() for k in vax.SERIES for f in ("mean", "lower", "upper")))
         t = torch.tensor([digest], dtype=torch.float64, device=f"cuda:{local}")
         lo, hi = t.clone(), t.clone()
@@ -56,7 +64,7 @@ def main():
             T = len(res[vax.SERIES[0]]["mean"])
             bounds = vax.model._bounds12(np.array(b[0]) / 100, np.array(b[1]) / 100, np.array(b[2]),
                                          np.array(b[3]), np.array(b[4]) / 100, np.array(b[5]) / 100)
-            cfg = nat.make_config(bounds, 50000, T, n, 20261020, (1 - ci / 100) / 2, (1 + ci / 100) / 2)
+            cfg = nat.make_config(bounds, N, T, n, 20261020, (1 - ci / 100) / 2, (1 + ci / 100) / 2)
             single = vax.default_context(local).run_bounds(cfg)                    # one GPU, no torch.distributed
             equal = all(np.array_equal(res[k][f], getattr(single, f)[s])
                         for s, k in enumerate(vax.SERIES) for f in ("mean", "lower", "upper"))
@@ -64,6 +72,7 @@ def main():
             ok_all = ok_all and ok
             print(json.dumps({"scenario": name, "n_gpus": world, "bit_identical_to_single_gpu": equal,
                               "identical_on_all_ranks": same_across_ranks, "passes": int(single.c.n_passes),
+                              "sharded_wall_ms": round(wall_ms, 3), "single_gpu_device_ms": round(float(single.c.device_ms), 3),
                               "agnostics": msg, "ok": ok}))
     usa = ([35, 45], [12, 25], [0.0, 0.02], [5, 7], [1, 1.2], [5, 10])
     dates = dict(start_date="2020-12-15", end_date="2022-07-1")
