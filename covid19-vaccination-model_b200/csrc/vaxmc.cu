@@ -179,6 +179,7 @@ struct vx_ctx {
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
     int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
+    int64_t select_global = 0;            // 1: always the global-memory radix select (tests: both kernels, same answers)
     int64_t side_samples = -1;            // samples stepped beside the pilot (-1: 2 x the pilot, <= 2^18; 0: none)
     int sm_count = 148;
     // pinned host staging for the copy-backs (a D2H copy into pageable memory blocks the host
@@ -532,7 +533,18 @@ int select_launch(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, 
       rc_ = pool_get(ctx, SLOT_SEL_SUMS, sizeof(long long) * rows, &p_); if (rc_) return rc_; d_sums = (long long *)p_;
       rc_ = hpin_get(ctx, HSLOT_SEL, sizeof(long long) * rows + sizeof(int32_t) * rows * K, &h); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, st));
-    vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
+    // rows that fit in shared memory (the pilot: 64 KB per row) are selected on chip after one read
+    const size_t smem = sizeof(int32_t) * (size_t)((n + 3) & ~(int64_t)3) + sizeof(uint32_t) * SELS_BINS;
+    if (smem <= 200 * 1024 && !ctx->select_global) {
+        static bool attr_set[64] = {false};
+        if (ctx->device < 64 && !attr_set[ctx->device]) {
+            CK(cudaFuncSetAttribute(vx_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set[ctx->device] = true;
+        }
+        vx_select_smem_kernel<<<(unsigned)rows, SELS_THREADS, smem, st>>>(d_data, ld, (int)n, d_ranks, K, d_out, d_sums);
+    } else {
+        vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
+    }
     CKL();
     CK(cudaMemcpyAsync(h, d_sums, sizeof(long long) * rows, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync((char *)h + sizeof(long long) * rows, d_out, sizeof(int32_t) * rows * K, cudaMemcpyDeviceToHost, st));
@@ -807,6 +819,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
     else if (s == "exact_poisson") ctx->exact_poisson = value != 0;
     else if (s == "side_samples") ctx->side_samples = (int64_t)value;
+    else if (s == "select_global") ctx->select_global = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }

@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 
 namespace vx {
 
@@ -203,8 +204,11 @@ __device__ __forceinline__ int poisson_invert(float lam, float u, int kmax)
 
 // The Poisson variate of the regime table above, given the pair's coefficients (WHICH = 0: first
 // draw of the day, 1: second).
+// `cap`: the caller clamps the variate to [0, cap] anyway (model.py:105-108, 117-118), so the
+// sequential search of the inversion regime may stop there (late in the campaign lam1 ~ 1.7 n_wait
+// with n_wait = 0, 1, 2: one comparison instead of a loop).
 template <int WHICH>
-__device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &c)
+__device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &c, int cap = 40)
 {
     float a0, b0, a1, b1, a2, b2, a3, b3, a4, b4;
     unpack2(c.c0, a0, b0); unpack2(c.c1, a1, b1); unpack2(c.c2, a2, b2);
@@ -216,7 +220,7 @@ __device__ __forceinline__ int poisson_draw_c(float lam, float z, const CFCoef &
     int x = max(__float2int_rd(fmaf(s, z, lam) + tail), 0);
     if (lam < POISSON_INV_MAX) {
         x = 0;
-        if (lam > 0.0f) x = poisson_invert(lam, normal_cdf(z), 40);
+        if (lam > 0.0f) x = poisson_invert(lam, normal_cdf(z), min(cap, 40));
     }
     return x;
 }
@@ -571,14 +575,15 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
             const CFCoef cf = cf_coefficients(z1, z2);
             // ---- vaccination draw, model.py:102-112
             const float lam1 = (float)n_wait * ((float)stock * c1);
+            const int cap1 = min(stock, n_wait);
             int dv = EXACT ? poisson_draw_exact(lam1, s_lo, s_hi, (uint32_t)day, 0u, a.keys)
-                           : poisson_draw_c<0>(lam1, z1, cf);
-            dv = min(dv, min(stock, n_wait));
+                           : poisson_draw_c<0>(lam1, z1, cf, cap1);
+            dv = min(dv, cap1);
             n_vacc += dv; n_wait -= dv; stock -= dv;
             // ---- conversion draw, model.py:115-120
             const float lam2 = (float)n_agn * ((float)n_vacc * c2);
             int da = EXACT ? poisson_draw_exact(lam2, s_lo, s_hi, (uint32_t)day, 1u, a.keys)
-                           : poisson_draw_c<1>(lam2, z2, cf);
+                           : poisson_draw_c<1>(lam2, z2, cf, n_agn);
             da = min(da, n_agn);
             n_agn -= da; n_wait += da;
             // ---- recording, model.py:124-127 and the weekly series :196-214
@@ -639,14 +644,14 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                 // a value inside one of the row's two windows: one more count in its bin
                 auto hit = [&](int v) {
                     const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
-                    bin_add_if(dl < wl.len, hist, wl.off + (dl >> wl.shift), a.bins64);
-                    bin_add_if(dh < wh.len, hist, wh.off + (dh >> wh.shift), a.bins64);
+                    if (dl < wl.len) bin_add(hist, wl.off + (dl >> wl.shift), a.bins64);
+                    if (dh < wh.len) bin_add(hist, wh.off + (dh >> wh.shift), a.bins64);
                 };
                 // In-window values are rare (the windows hold ~1-3 % of the mass), but with 32
                 // rows in flight SOME lane has one in almost every step: the scan is branch-free
-                // (one combined test per 4 samples sets a bit) and the quads with a hit are
-                // revisited afterwards, so the divergent part runs max-over-lanes(#hit quads)
-                // times per tile (~3) instead of once per step (8).
+                // and only marks the quads of samples that hit; the marked quads are revisited
+                // afterwards, so the divergent part runs max-over-lanes(#hit quads) times per tile
+                // (~3) instead of once per scan step (8).
                 uint32_t hits = 0;
                 auto scan4 = [&](const int s) {
                     const int4 v4 = *reinterpret_cast<const int4 *>(row + s);
@@ -656,17 +661,23 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                     const uint32_t h0 = v0 - wh.a, h1 = v1 - wh.a, h2 = v2 - wh.a, h3 = v3 - wh.a;
                     clo += (l0 >> 31) + (l1 >> 31) + (l2 >> 31) + (l3 >> 31);
                     chi += (h0 >> 31) + (h1 >> 31) + (h2 >> 31) + (h3 >> 31);
+#ifdef VX_HITS_PER_VALUE
+                    if (l0 < wl.len || h0 < wh.len) hits |= 1u << s;
+                    if (l1 < wl.len || h1 < wh.len) hits |= 2u << s;
+                    if (l2 < wl.len || h2 < wh.len) hits |= 4u << s;
+                    if (l3 < wl.len || h3 < wh.len) hits |= 8u << s;
+#else
+                    // one combined test per 4 samples (marking single samples costs 10 more instructions
+                    // per quad than it saves in the revisit loop: measured)
                     const uint32_t ml = min(min(l0, l1), min(l2, l3)), mh = min(min(h0, h1), min(h2, h3));
                     if (ml < wl.len || mh < wh.len) hits |= 1u << (s >> 2);
+#endif
                 };
                 if (nvalid == 32) {
 #pragma unroll
                     for (int s = 0; s < 32; s += 4) scan4(s);
                 } else {
-                    int s = 0;
-#pragma unroll 1
-                    for (; s + 4 <= nvalid; s += 4) scan4(s);
-                    for (; s < nvalid; ++s) {
+                    for (int s = 0; s < nvalid; ++s) {
                         const int v = row[s];
                         sum += (uint32_t)v;
                         clo += (uint32_t)(v - wl.a) >> 31;
@@ -675,10 +686,14 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
                     }
                 }
                 while (hits) {
-                    const int qd = __ffs((int)hits) - 1;
+                    const int sidx = __ffs((int)hits) - 1;
                     hits &= hits - 1;
-                    const int4 v4 = *reinterpret_cast<const int4 *>(row + 4 * qd);
+#ifdef VX_HITS_PER_VALUE
+                    hit(row[sidx]);
+#else
+                    const int4 v4 = *reinterpret_cast<const int4 *>(row + 4 * sidx);
                     hit(v4.x); hit(v4.y); hit(v4.z); hit(v4.w);
+#endif
                 }
                 atomicAdd(a.acc + ACC_HDR + grow, (unsigned long long)sum);
                 if (clo) atomicAdd(a.acc + ACC_HDR + R + 2 * grow, (unsigned long long)clo);
@@ -705,14 +720,27 @@ __global__ void __launch_bounds__(256) vx_fold_matrix_kernel(const int32_t *__re
     unsigned long long *hist = acc + ACC_HDR + 3 * (int64_t)R;
     const int32_t *src = dump + (int64_t)row * ld;
     unsigned long long sum = 0, clo = 0, chi = 0;
-    for (int64_t c = c0 + threadIdx.x; c < c1; c += 256) {
-        const int v = src[c];
+    auto one = [&](const int v) {
         sum += (unsigned long long)(uint32_t)v;
         const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
         clo += dl >> 31; chi += dh >> 31;
         if (dl < wl.len) bin_add(hist, wl.off + (dl >> wl.shift), bins64);
         if (dh < wh.len) bin_add(hist, wh.off + (dh >> wh.shift), bins64);
+    };
+    // 16-byte loads, two in flight per thread (HBM/L2 streaming: this kernel only reads)
+    int64_t c = c0;
+    if (((ld | c0) & 3) == 0) {
+        const int4 *src4 = reinterpret_cast<const int4 *>(src + c0);
+        const int64_t n4 = (c1 - c0) / 4;
+        int64_t i = threadIdx.x;
+        for (; i + 256 < n4; i += 512) {
+            const int4 a = src4[i], b = src4[i + 256];
+            one(a.x); one(a.y); one(a.z); one(a.w); one(b.x); one(b.y); one(b.z); one(b.w);
+        }
+        for (; i < n4; i += 256) { const int4 a = src4[i]; one(a.x); one(a.y); one(a.z); one(a.w); }
+        c = c0 + 4 * n4;
     }
+    for (c += threadIdx.x; c < c1; c += 256) one(src[c]);
     sh[0][threadIdx.x] = sum; sh[1][threadIdx.x] = clo; sh[2][threadIdx.x] = chi;
     __syncthreads();
     for (int off = 128; off > 0; off >>= 1) {
@@ -964,6 +992,174 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
     __syncthreads();
     block_radix_select<T>(row, n, nranks, S, first_key, diff);
     if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(S.prefix[tid]);
+}
+
+// The same order statistics for rows that fit in shared memory (the pilot matrix: 16384 columns =
+// 64 KB per row).  The row is read from HBM/L2 ONCE into shared memory (row sum, min and max on the
+// way), then located by histogram refinement entirely on chip: 4096 bins over [min, max] first,
+// then, if a bin is wider than one value, all still-open ranks at once with 4096 / #ranks bins
+// each over their bins -- two levels resolve a range of 2^22+, three any int32 row.  ~6
+// instructions per element and level against ~25 per element and 8-bit digit of the
+// global-memory kernel above, which stays for rows that do not fit.
+constexpr int SELS_THREADS = 512;
+constexpr int SELS_BINS = 4096;
+
+__global__ void __launch_bounds__(SELS_THREADS) vx_select_smem_kernel(
+    const int32_t *__restrict__ data, int64_t ld, int n, const int64_t *__restrict__ ranks, int nranks,
+    int32_t *__restrict__ out /*[rows][nranks]*/, long long *__restrict__ sums /*[rows]*/)
+{
+    extern __shared__ __align__(16) int sels_sm[];
+    int *vals = sels_sm;                                            // [n rounded up to 4]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sels_sm + ((n + 3) & ~3));   // [SELS_BINS]
+    __shared__ long long red_sum[SELS_THREADS / 32];
+    __shared__ int red_min[SELS_THREADS / 32], red_max[SELS_THREADS / 32];
+    __shared__ uint32_t warp_tot[SELS_THREADS / 32];
+    __shared__ long long t_lo[SEL_MAXR], t_w[SEL_MAXR], t_rem[SEL_MAXR];   // open interval [lo, lo+w) and rank inside it
+    __shared__ int t_shift[SEL_MAXR], t_slot[SEL_MAXR], t_open[SEL_MAXR];
+    __shared__ long long s_lo[SEL_MAXR], s_w[SEL_MAXR];             // distinct intervals of this level
+    __shared__ int s_shift[SEL_MAXR], s_n;
+    __shared__ long long u_lo[SEL_MAXR], u_w[SEL_MAXR], u_rem[SEL_MAXR];   // next level's intervals (written by the bin owners)
+    __shared__ uint32_t slot_base[SEL_MAXR];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int32_t *row = data + (int64_t)blockIdx.x * ld;
+
+    // ---- stage the row; sum / min / max
+    long long acc = 0;
+    int mn = INT_MAX, mx = INT_MIN;
+    if (((ld | (int64_t)n) & 3) == 0) {
+        const int4 *src = reinterpret_cast<const int4 *>(row);
+        for (int i = tid; i < n / 4; i += SELS_THREADS) {
+            const int4 v = src[i];
+            reinterpret_cast<int4 *>(vals)[i] = v;
+            acc += (long long)v.x + v.y + v.z + v.w;
+            mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
+            mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
+        }
+    } else {
+        for (int i = tid; i < n; i += SELS_THREADS) {
+            const int v = row[i];
+            vals[i] = v; acc += v; mn = min(mn, v); mx = max(mx, v);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { red_sum[wid] = acc; red_min[wid] = mn; red_max[wid] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+        long long a = 0; int lo = INT_MAX, hi = INT_MIN;
+        for (int w = 0; w < SELS_THREADS / 32; ++w) { a += red_sum[w]; lo = min(lo, red_min[w]); hi = max(hi, red_max[w]); }
+        if (sums) sums[blockIdx.x] = a;
+        for (int k = 0; k < nranks; ++k) {
+            t_lo[k] = lo; t_w[k] = (long long)hi - lo + 1; t_rem[k] = ranks[k]; t_open[k] = t_w[k] > 1;
+        }
+    }
+    __syncthreads();
+
+    for (int level = 0; level < 8; ++level) {
+        // ---- distinct open intervals of this level, SELS_BINS / (their number, rounded up to 2^k) bins each
+        if (tid == 0) {
+            int nd = 0;
+            for (int k = 0; k < nranks; ++k) {
+                if (!t_open[k]) { t_slot[k] = -1; continue; }
+                int f = -1;
+                for (int d = 0; d < nd; ++d) if (s_lo[d] == t_lo[k]) { f = d; break; }
+                if (f < 0) { f = nd; s_lo[nd] = t_lo[k]; s_w[nd] = t_w[k]; ++nd; }
+                t_slot[k] = f;
+            }
+            s_n = nd;
+            int per = SELS_BINS;
+            while (per * nd > SELS_BINS) per >>= 1;            // nd <= 8 -> per >= 512
+            for (int d = 0; d < nd; ++d) {
+                int sh = 0;
+                while (((s_w[d] + ((1ll << sh) - 1)) >> sh) > per) ++sh;
+                s_shift[d] = sh;
+            }
+            for (int k = 0; k < nranks; ++k) if (t_slot[k] >= 0) t_shift[k] = s_shift[t_slot[k]];
+        }
+        __syncthreads();
+        const int nd = s_n;
+        if (nd == 0) break;
+        int per = SELS_BINS;
+        while (per * nd > SELS_BINS) per >>= 1;
+        for (int i = tid; i < SELS_BINS; i += SELS_THREADS) hist[i] = 0;
+        __syncthreads();
+        // ---- histogram of the values inside the open intervals
+        if (nd == 1) {
+            const long long lo = s_lo[0], w = s_w[0];
+            const int sh = s_shift[0];
+            for (int i0 = 0; i0 < n; i0 += SELS_THREADS) {
+                const int i = i0 + tid;
+                const bool in = i < n;
+                const long long d = in ? (long long)vals[i] - lo : -1;
+                const bool hit = in && d >= 0 && d < w;
+                const uint32_t b = hit ? (uint32_t)(d >> sh) : 0xffffffffu;
+                // flat rows: the whole warp in one bin -> one atomic instead of 32 serialised ones
+                const uint32_t b0 = __shfl_sync(0xffffffffu, b, 0);
+                if (__all_sync(0xffffffffu, b == b0)) {
+                    if (lane == 0 && b0 != 0xffffffffu) atomicAdd(&hist[b0], 32u);
+                } else if (hit) {
+                    atomicAdd(&hist[b], 1u);
+                }
+            }
+        } else {
+            for (int i = tid; i < n; i += SELS_THREADS) {
+                const long long v = vals[i];
+                for (int d = 0; d < nd; ++d) {
+                    const long long dd = v - s_lo[d];
+                    if (dd >= 0 && dd < s_w[d]) { atomicAdd(&hist[d * per + (int)(dd >> s_shift[d])], 1u); break; }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- exclusive scan of the SELS_BINS counts (8 per thread), restarted at every interval's first bin
+        uint32_t c[SELS_BINS / SELS_THREADS], tsum = 0;
+#pragma unroll
+        for (int q = 0; q < SELS_BINS / SELS_THREADS; ++q) { c[q] = hist[tid * (SELS_BINS / SELS_THREADS) + q]; tsum += c[q]; }
+        uint32_t incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < wid; ++w) base += warp_tot[w];
+        const uint32_t excl_global = base + incl - tsum;        // values in bins before this thread's first bin
+        // the interval that owns this thread's bins starts at bin slot*per: its own offset = the count before it
+        const int my_slot = (tid * (SELS_BINS / SELS_THREADS)) / per;
+        if ((tid * (SELS_BINS / SELS_THREADS)) % per == 0 && my_slot < nd) slot_base[my_slot] = excl_global;
+        __syncthreads();
+        if (my_slot < nd) {
+            uint32_t run = excl_global - slot_base[my_slot];    // count inside the interval before this thread's bins
+#pragma unroll
+            for (int q = 0; q < SELS_BINS / SELS_THREADS; ++q) {
+                const int bin = tid * (SELS_BINS / SELS_THREADS) + q - my_slot * per;
+                for (int k = 0; k < nranks; ++k) {
+                    if (t_slot[k] != my_slot) continue;
+                    const long long r = t_rem[k];
+                    if (r >= (long long)run && r < (long long)run + c[q]) {
+                        // exactly one (thread, q) matches rank k; the t_* arrays are still being read by the
+                        // other threads, so the new interval goes to u_* and is adopted after the barrier
+                        const int sh = t_shift[k];
+                        const long long nlo = t_lo[k] + ((long long)bin << sh);
+                        u_lo[k] = nlo; u_w[k] = min(1ll << sh, t_lo[k] + t_w[k] - nlo); u_rem[k] = r - run;
+                    }
+                }
+                run += c[q];
+            }
+        }
+        __syncthreads();
+        if (tid < nranks && t_slot[tid] >= 0) {
+            t_lo[tid] = u_lo[tid]; t_w[tid] = u_w[tid]; t_rem[tid] = u_rem[tid]; t_open[tid] = u_w[tid] > 1;
+        }
+        __syncthreads();
+    }
+    if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = (int32_t)t_lo[tid];
 }
 
 // --------------------------------------------- order statistics out of merged windows

@@ -8,7 +8,7 @@ CUDA behind the C ABI of include/vaxmc.h):
     run_sampling               model.py:139-228   (explicit parameter tuples)
     sample_param_combinations  model.py:231-303
     run_single_realization     model.py:29-136
-    main / SplitArgsStr / SplitArgsFloat   model.py:371-546  (flags verbatim)
+    main / SplitArgsStr / SplitArgsFloat   model.py:371-546  (same flags and parsing)
 
 What differs, on purpose:
   * randomness is Philox4x32-10 keyed by (seed, global sample id) instead of numpy's global
@@ -360,7 +360,10 @@ class SplitArgsFloat(argparse.Action):
 
 
 def build_parser() -> argparse.ArgumentParser:
-    """The reference's flags, byte for byte (model.py:419-500), plus optional additions."""
+    """The reference's flags (model.py:419-500): same names, same split-on-comma actions, same types
+    and required-ness, the same defaults for --mc_samples (100) and --CI (0.95).  The defaults of
+    the seven `required=True` flags can never take effect in either program and the help texts
+    are worded independently.  Optional additions follow (none changes the reference's flags)."""
     parser = argparse.ArgumentParser(
         description="Model of the COVID-19 vaccination campaign (B200-native Monte Carlo path)")
     parser.add_argument("--pro", type=str, action=SplitArgsFloat, default=[30.0, 40.0], required=True,

@@ -133,6 +133,27 @@ def test_radix_select_exact(ctx):
         rk = sorted({0, m // 2, m - 1})
         got, sums = ctx.test_select(d, rk)
         assert np.array_equal(got, np.sort(d, axis=1)[:, rk]), m
+    # the two kernels (rows staged in shared memory up to ~47k columns; radix passes over global
+    # memory above) on the same data: wide ranges (three histogram levels), negatives, int32 extremes,
+    # duplicate ranks, odd row lengths (unaligned rows take the scalar load path)
+    for n in (16384, 16383, 47000, 47104, 1000):
+        data = np.stack([
+            rng.integers(-(1 << 31), (1 << 31) - 1, n), rng.integers(0, 1 << 27, n), rng.integers(-5, 5, n),
+            np.full(n, -(1 << 31)), np.full(n, (1 << 31) - 1), rng.poisson(40, n), rng.poisson(3e5, n),
+            np.where(rng.random(n) < 0.5, -(1 << 31), (1 << 31) - 1), rng.integers(0, 4097, n),
+            (rng.integers(0, 3, n) * (1 << 22)) + rng.integers(0, 2, n),
+        ]).astype(np.int32)
+        ranks = [0, 0, n // 40, n // 40 + 1, n // 2, n // 2, n - 2, n - 1]
+        want = np.sort(data, axis=1)[:, ranks]
+        try:
+            outs = []
+            for g in (0, 1):
+                ctx.set_option("select_global", g)
+                got, sums = ctx.test_select(data, ranks)
+                assert np.array_equal(got, want), (n, g)
+                assert np.array_equal(sums, data.astype(np.int64).sum(axis=1)), (n, g)
+        finally:
+            ctx.set_option("select_global", 0)
 
 
 # ------------------------------------------------------ (1) expected-value parity
