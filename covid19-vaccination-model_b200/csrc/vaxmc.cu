@@ -179,6 +179,7 @@ struct vx_ctx {
     int64_t sort_samples = 1;
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
     int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
+    int64_t pipe_pilot = 1;               // latency variant of the stepper for launches that cannot fill the GPU
     int64_t select_global = 0;            // 1: always the global-memory radix select (tests: both kernels, same answers)
     int64_t side_samples = -1;            // samples stepped beside the pilot (-1: 2 x the pilot, <= 2^18; 0: none)
     int sm_count = 148;
@@ -539,6 +540,8 @@ int select_launch(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, 
         static bool attr_set[64] = {false};
         if (ctx->device < 64 && !attr_set[ctx->device]) {
             CK(cudaFuncSetAttribute(vx_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            // all of the SM's L1/shared array as shared memory: two 80 KB rows resident per SM
+            CK(cudaFuncSetAttribute(vx_select_smem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             attr_set[ctx->device] = true;
         }
         vx_select_smem_kernel<<<(unsigned)rows, SELS_THREADS, smem, st>>>(d_data, ld, (int)n, d_ranks, K, d_out, d_sums);
@@ -582,12 +585,15 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
                 int32_t *d_dump, int64_t ld, cudaStream_t st = nullptr, const int32_t *d_perm = nullptr)
 {
     if (!st) st = ctx->stream;
+    // a launch that cannot fill the GPU is a serial T-day chain per warp: take the latency variant
+    const bool latency = ctx->pipe_pilot && count <= (int64_t)ctx->sm_count * 4 * SIM_THREADS;
     SimArgs a = make_args(j, first, count, d_params);
     a.dump = d_dump;
     a.dump_stride = ld;
     a.perm = d_perm;
     const int64_t grid = (count + SIM_THREADS - 1) / SIM_THREADS;
     if (ctx->exact_poisson) vx_sim_kernel<SIM_DUMP, 1><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
+    else if (latency) vx_sim_kernel<SIM_DUMP, 0, 1><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
     else vx_sim_kernel<SIM_DUMP, 0><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
     CKL();
     return VX_OK;
@@ -820,6 +826,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "exact_poisson") ctx->exact_poisson = value != 0;
     else if (s == "side_samples") ctx->side_samples = (int64_t)value;
     else if (s == "select_global") ctx->select_global = value != 0;
+    else if (s == "pipe_pilot") ctx->pipe_pilot = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;
 }

@@ -510,8 +510,13 @@ constexpr int SIM_THREADS = 128;       // warps are independent: small CTAs = sh
 
 enum { SIM_DUMP = 0, SIM_FOLD = 1 };
 
-template <int MODE, int EXACT = 0>
-__global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_sim_kernel(const SimArgs a)
+// PIPE = 1 is the LATENCY variant for launches that cannot fill the GPU (the pilot: 128 CTAs, one
+// warp per scheduler, a serial T-day chain): the state-independent half of a day pair -- Philox,
+// Box-Muller, the packed z-polynomials -- is computed one pair ahead, so that it sits in the
+// same straight-line code as the state-dependent chain of the current pair and fills its stall
+// slots.  It needs ~50 more registers, which only an occupancy-bound launch would miss.
+template <int MODE, int EXACT = 0, int PIPE = 0>
+__global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MINBLOCKS)) vx_sim_kernel(const SimArgs a)
 {
     __shared__ __align__(16) int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -553,6 +558,18 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
     int q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;            // delta_n_vacc of days = 5 (mod 7), 5 weeks deep
 
     const int T = a.T, W = a.W;
+    struct PairRng { float z1, z2, z3, z4; CFCoef cfA, cfB; };
+    auto pair_ahead = [&](const uint32_t pair) {
+        PairRng o;
+        const uint4 r = philox4x32_10(s_lo, s_hi, pair, TAG_DAY, a.keys);
+        normal_pair(r.x, r.y, o.z1, o.z2);
+        normal_pair(r.z, r.w, o.z3, o.z4);
+        o.cfA = cf_coefficients(o.z1, o.z2);
+        o.cfB = cf_coefficients(o.z3, o.z4);
+        return o;
+    };
+    PairRng nx;
+    if (PIPE) nx = pair_ahead(0u);
     for (int d0 = 0; d0 < T; d0 += WIN_DAYS) {
         int *tp = tile + lane;                              // this sample's column of the tile
         const int nd = min(WIN_DAYS, T - d0);               // days in this tile
@@ -571,8 +588,7 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
         };
         // one day of model.py:82-127; (z1, z2) = the day's two normals.  WEEK0: day % 7 == 0
         // (arrivals already added; the weekly rows are recorded), wk = week slot of the tile
-        auto day_step = [&](const int day, const float z1, const float z2, const bool week0, const int wk) {
-            const CFCoef cf = cf_coefficients(z1, z2);
+        auto day_step = [&](const int day, const float z1, const float z2, const CFCoef &cf, const bool week0, const int wk) {
             // ---- vaccination draw, model.py:102-112
             const float lam1 = (float)n_wait * ((float)stock * c1);
             const int cap1 = min(stock, n_wait);
@@ -614,17 +630,31 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : VX_SIM_MINBLOCKS) vx_
 #pragma unroll 1
         for (int pp = 0; 2 * pp < nd; ++pp) {
             const int dayA = d0 + 2 * pp;
-            const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)dayA >> 1, TAG_DAY, a.keys);
-            float z1, z2;
-            normal_pair(r.x, r.y, z1, z2);
-            if (pp == 0) arrivals(dayA);
-            const int dvA = day_step(dayA, z1, z2, pp == 0, 0);
-            if (pp == 6) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvA; }     // tile day 12 = 5 (mod 7)
-            if (2 * pp + 1 < nd) {
-                normal_pair(r.z, r.w, z1, z2);
-                if (pp == 3) arrivals(dayA + 1);                                // tile day 7
-                const int dvB = day_step(dayA + 1, z1, z2, pp == 3, 1);
-                if (pp == 2) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvB; }  // tile day 5
+            if (PIPE) {
+                const PairRng cur = nx;
+                nx = pair_ahead(((uint32_t)dayA >> 1) + 1u);                     // next pair, state-independent
+                if (pp == 0) arrivals(dayA);
+                const int dvA = day_step(dayA, cur.z1, cur.z2, cur.cfA, pp == 0, 0);
+                if (pp == 6) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvA; }
+                if (2 * pp + 1 < nd) {
+                    if (pp == 3) arrivals(dayA + 1);
+                    const int dvB = day_step(dayA + 1, cur.z3, cur.z4, cur.cfB, pp == 3, 1);
+                    if (pp == 2) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvB; }
+                }
+            } else {
+                const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)dayA >> 1, TAG_DAY, a.keys);
+                float z1, z2;
+                normal_pair(r.x, r.y, z1, z2);
+                if (pp == 0) arrivals(dayA);
+                const int dvA = day_step(dayA, z1, z2, cf_coefficients(z1, z2), pp == 0, 0);
+                if (pp == 6) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvA; }     // tile day 12 = 5 (mod 7)
+                if (2 * pp + 1 < nd) {
+                    // day B's normals are made only now: ten fewer live registers across day A
+                    normal_pair(r.z, r.w, z1, z2);
+                    if (pp == 3) arrivals(dayA + 1);                                // tile day 7
+                    const int dvB = day_step(dayA + 1, z1, z2, cf_coefficients(z1, z2), pp == 3, 1);
+                    if (pp == 2) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvB; }  // tile day 5
+                }
             }
         }
         if (MODE == SIM_FOLD) {
@@ -1004,7 +1034,7 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
 constexpr int SELS_THREADS = 512;
 constexpr int SELS_BINS = 4096;
 
-__global__ void __launch_bounds__(SELS_THREADS) vx_select_smem_kernel(
+__global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_smem_kernel(
     const int32_t *__restrict__ data, int64_t ld, int n, const int64_t *__restrict__ ranks, int nranks,
     int32_t *__restrict__ out /*[rows][nranks]*/, long long *__restrict__ sums /*[rows]*/)
 {
@@ -1134,23 +1164,25 @@ __global__ void __launch_bounds__(SELS_THREADS) vx_select_smem_kernel(
         const int my_slot = (tid * (SELS_BINS / SELS_THREADS)) / per;
         if ((tid * (SELS_BINS / SELS_THREADS)) % per == 0 && my_slot < nd) slot_base[my_slot] = excl_global;
         __syncthreads();
-        if (my_slot < nd) {
+        if (my_slot < nd && tsum > 0) {
             uint32_t run = excl_global - slot_base[my_slot];    // count inside the interval before this thread's bins
+            for (int k = 0; k < nranks; ++k) {
+                if (t_slot[k] != my_slot) continue;
+                const long long r = t_rem[k];
+                if (r < (long long)run || r >= (long long)run + tsum) continue;     // not in this thread's bins
+                uint32_t before = run;
 #pragma unroll
-            for (int q = 0; q < SELS_BINS / SELS_THREADS; ++q) {
-                const int bin = tid * (SELS_BINS / SELS_THREADS) + q - my_slot * per;
-                for (int k = 0; k < nranks; ++k) {
-                    if (t_slot[k] != my_slot) continue;
-                    const long long r = t_rem[k];
-                    if (r >= (long long)run && r < (long long)run + c[q]) {
+                for (int q = 0; q < SELS_BINS / SELS_THREADS; ++q) {
+                    if (r >= (long long)before && r < (long long)before + c[q]) {
                         // exactly one (thread, q) matches rank k; the t_* arrays are still being read by the
                         // other threads, so the new interval goes to u_* and is adopted after the barrier
+                        const int bin = tid * (SELS_BINS / SELS_THREADS) + q - my_slot * per;
                         const int sh = t_shift[k];
                         const long long nlo = t_lo[k] + ((long long)bin << sh);
-                        u_lo[k] = nlo; u_w[k] = min(1ll << sh, t_lo[k] + t_w[k] - nlo); u_rem[k] = r - run;
+                        u_lo[k] = nlo; u_w[k] = min(1ll << sh, t_lo[k] + t_w[k] - nlo); u_rem[k] = r - before;
                     }
+                    before += c[q];
                 }
-                run += c[q];
             }
         }
         __syncthreads();
