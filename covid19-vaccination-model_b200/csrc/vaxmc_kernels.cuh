@@ -177,14 +177,15 @@ struct CFCoef { f32x2 c0, c1, c2, c3, c4; };
 
 __device__ __forceinline__ CFCoef cf_coefficients(float z1, float z2)
 {
+    // (no clamp of z in the two fitted orders: |z| > 5 has probability 5.7e-7 and the law's error
+    //  there is the same with and without it -- oracle/fit_poisson_cf.py prints both)
     const f32x2 z = pack2(z1, z2), z2p = mul2(z, z);
-    const f32x2 zc = pack2(fminf(fmaxf(z1, -5.0f), 5.0f), fminf(fmaxf(z2, -5.0f), 5.0f)), zc2 = mul2(zc, zc);
     CFCoef c;
     c.c0 = fma2(z2p, splat2(0.16666667f), splat2(0.33333334f));
     c.c1 = mul2(z, fma2(z2p, splat2(-0.013888889f), splat2(-0.027777778f)));
     c.c2 = fma2(z2p, fma2(z2p, splat2(0.0037037036f), splat2(0.0086419750f)), splat2(-0.019753087f));
-    c.c3 = mul2(zc, fma2(zc2, fma2(zc2, splat2(CF_A5), splat2(CF_A3)), splat2(CF_A1)));
-    c.c4 = fma2(zc2, fma2(zc2, fma2(zc2, splat2(CF_B6), splat2(CF_B4)), splat2(CF_B2)), splat2(CF_B0));
+    c.c3 = mul2(z, fma2(z2p, fma2(z2p, splat2(CF_A5), splat2(CF_A3)), splat2(CF_A1)));
+    c.c4 = fma2(z2p, fma2(z2p, fma2(z2p, splat2(CF_B6), splat2(CF_B4)), splat2(CF_B2)), splat2(CF_B0));
     return c;
 }
 
@@ -519,6 +520,8 @@ template <int MODE, int EXACT = 0, int PIPE = 0>
 __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MINBLOCKS)) vx_sim_kernel(const SimArgs a)
 {
     __shared__ __align__(16) int tile_all[MODE == SIM_FOLD ? (SIM_THREADS / 32) * 32 * TILE_LD : 4];
+    __shared__ double arr_sm[3][SIM_THREADS];   // nv0, nvmax, tau*7: read once a week (until the cap is reached)
+    __shared__ int q_sm[5][SIM_THREADS];        // delay line of delta_n_vacc, one push a week
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // (a persistent launch with warps claiming 32-sample batches from a counter was tried:
     //  4 % slower than letting the hardware schedule 128-thread CTAs)
@@ -555,7 +558,16 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
     const int arr_cap = (int)(p.nvmax * Nd);
     const float c1 = (float)((2.0 / 7.0) / Nd);            // (2/7)/N   model.py:102
     const float c2 = (float)(p.pressure / Nd);             // pressure/N model.py:112-115
-    int q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;            // delta_n_vacc of days = 5 (mod 7), 5 weeks deep
+    // delta_n_vacc of days = 5 (mod 7), 5 weeks deep: the weekly series adds the value of day 7k-30,
+    // i.e. the push of week k-5, to day 7k's (model.py:196-209)
+    // ... kept as a ring in shared memory (slot = week % 5; one load and one store a week), together
+    // with the fp64 arrival parameters (read once a week): 11 registers the daily chain does not
+    // need, which leaves ptxas room to schedule it (62 -> 55 registers, fold 1.7 % faster on B200)
+    arr_sm[0][threadIdx.x] = p.nv0; arr_sm[1][threadIdx.x] = p.nvmax; arr_sm[2][threadIdx.x] = tau7;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) q_sm[k][threadIdx.x] = 0;
+    auto q_oldest = [&](const int week) { return q_sm[week % 5][threadIdx.x]; };
+    auto q_push = [&](const int week, const int dv) { q_sm[week % 5][threadIdx.x] = dv; };
 
     const int T = a.T, W = a.W;
     struct PairRng { float z1, z2, z3, z4; CFCoef cfA, cfB; };
@@ -579,9 +591,10 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
             if (capped) {
                 arr = arr_cap;
             } else {
-                const double g = p.nv0 * exp(ln2 * (double)day / tau7);
-                const bool over = p.nvmax < g;              // Python min(g, nv_max)
-                arr = (int)((over ? p.nvmax : g) * Nd);
+                const double nv0 = arr_sm[0][threadIdx.x], nvmax = arr_sm[1][threadIdx.x], t7 = arr_sm[2][threadIdx.x];
+                const double g = nv0 * exp(ln2 * (double)day / t7);
+                const bool over = nvmax < g;                // Python min(g, nv_max)
+                arr = (int)((over ? nvmax : g) * Nd);
                 capped = over && monotone;
             }
             stock += arr;                                   // received == n_vacc + stock at all times
@@ -608,7 +621,7 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
                 tp[14 * TILE_LD] = stock;
                 tp += TILE_LD;
                 if (week0) {
-                    tile[(28 + wk) * TILE_LD + lane] = dv + q0;
+                    tile[(28 + wk) * TILE_LD + lane] = dv + q_oldest(d0 / 7 + wk);
                     tile[(30 + wk) * TILE_LD + lane] = n_vacc + stock;
                 }
             } else if (live) {
@@ -617,7 +630,7 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
                 a.dump[((int64_t)T + 2 * W + day) * ld + col] = stock;
                 if (week0) {
                     const int k = day / 7;
-                    a.dump[((int64_t)T + k) * ld + col] = dv + q0;
+                    a.dump[((int64_t)T + k) * ld + col] = dv + q_oldest(k);
                     a.dump[((int64_t)T + W + k) * ld + col] = n_vacc + stock;
                 }
             }
@@ -635,11 +648,11 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
                 nx = pair_ahead(((uint32_t)dayA >> 1) + 1u);                     // next pair, state-independent
                 if (pp == 0) arrivals(dayA);
                 const int dvA = day_step(dayA, cur.z1, cur.z2, cur.cfA, pp == 0, 0);
-                if (pp == 6) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvA; }
+                if (pp == 6) q_push(d0 / 7 + 1, dvA);
                 if (2 * pp + 1 < nd) {
                     if (pp == 3) arrivals(dayA + 1);
                     const int dvB = day_step(dayA + 1, cur.z3, cur.z4, cur.cfB, pp == 3, 1);
-                    if (pp == 2) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvB; }
+                    if (pp == 2) q_push(d0 / 7, dvB);
                 }
             } else {
                 const uint4 r = philox4x32_10(s_lo, s_hi, (uint32_t)dayA >> 1, TAG_DAY, a.keys);
@@ -647,13 +660,13 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
                 normal_pair(r.x, r.y, z1, z2);
                 if (pp == 0) arrivals(dayA);
                 const int dvA = day_step(dayA, z1, z2, cf_coefficients(z1, z2), pp == 0, 0);
-                if (pp == 6) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvA; }     // tile day 12 = 5 (mod 7)
+                if (pp == 6) q_push(d0 / 7 + 1, dvA);                             // tile day 12 = 5 (mod 7)
                 if (2 * pp + 1 < nd) {
                     // day B's normals are made only now: ten fewer live registers across day A
                     normal_pair(r.z, r.w, z1, z2);
                     if (pp == 3) arrivals(dayA + 1);                                // tile day 7
                     const int dvB = day_step(dayA + 1, z1, z2, cf_coefficients(z1, z2), pp == 3, 1);
-                    if (pp == 2) { q0 = q1; q1 = q2; q2 = q3; q3 = q4; q4 = dvB; }  // tile day 5
+                    if (pp == 2) q_push(d0 / 7, dvB);                            // tile day 5
                 }
             }
         }

@@ -29,8 +29,10 @@ def q3(z, lam):
             + (-8 / 405 + 7 * z * z / 810 + z ** 4 / 270) / lam)
 
 
-def q5(z, lam, a, b, zclamp=5.0):
-    zc = np.clip(z, -zclamp, zclamp)
+def q5(z, lam, a, b, zclamp=None):
+    # the kernel does not clamp z in the two fitted orders (an earlier version did, at +-5: the
+    # law's error is the same either way, see main())
+    zc = z if zclamp is None else np.clip(z, -zclamp, zclamp)
     return (q3(z, lam) + (a[0] * zc + a[1] * zc ** 3 + a[2] * zc ** 5) / lam ** 1.5
             + (b[0] + b[1] * zc ** 2 + b[2] * zc ** 4 + b[3] * zc ** 6) / lam ** 2)
 
@@ -79,7 +81,8 @@ def main():
     for lam in (2, 2.5, 3, 4, 5, 6, 8, 10, 16, 32, 100, 1000, 10000):
         e3, _ = law_error(lam, q3)
         e5, c5 = law_error(lam, lambda z, l: q5(z, l, a, b))
-        print(f"{lam:7g} {e3:18.2e} {e5:18.2e} {c5:15.1e}")
+        e5c, _ = law_error(lam, lambda z, l: q5(z, l, a, b, zclamp=5.0))
+        print(f"{lam:7g} {e3:18.2e} {e5:18.2e} {c5:15.1e}   (z clamped at +-5: {e5c:.2e})")
 
 
 if __name__ == "__main__":
