@@ -167,7 +167,9 @@ struct vx_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // regime sort runs here, under the latency-bound pilot
-    cudaEvent_t side_done = nullptr;
+    cudaEvent_t side_done = nullptr;      // everything queued on the side stream so far has finished
+    cudaEvent_t ev_sorted = nullptr;      // regime sort of the fold's samples done (side stream)
+    cudaEvent_t ev_wins = nullptr;        // window table uploaded and slab cleared (main stream)
     std::string err;
     int64_t launches = 0;
     Job *job = nullptr;
@@ -181,7 +183,8 @@ struct vx_ctx {
     int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
     int64_t pipe_pilot = 1;               // latency variant of the stepper for launches that cannot fill the GPU
     int64_t select_global = 0;            // 1: always the global-memory radix select (tests: both kernels, same answers)
-    int64_t side_samples = -1;            // samples stepped beside the pilot (-1: 2 x the pilot, <= 2^18; 0: none)
+    int64_t side_samples = -1;            // samples stepped beside the pilot (-1 = default = 0: none, see pilot_launch)
+    int64_t side_pad_smem = 0;            // experiment knob: dynamic smem of the side DUMP launch (limits its CTAs per SM)
     int sm_count = 148;
     // pinned host staging for the copy-backs (a D2H copy into pageable memory blocks the host
     // until it is done, which would serialise the batched grid driver)
@@ -582,7 +585,8 @@ int need_device(vx_ctx *ctx)
 }
 
 int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double *d_params,
-                int32_t *d_dump, int64_t ld, cudaStream_t st = nullptr, const int32_t *d_perm = nullptr)
+                int32_t *d_dump, int64_t ld, cudaStream_t st = nullptr, const int32_t *d_perm = nullptr,
+                size_t pad_smem = 0)
 {
     if (!st) st = ctx->stream;
     // a launch that cannot fill the GPU is a serial T-day chain per warp: take the latency variant
@@ -594,7 +598,7 @@ int launch_dump(vx_ctx *ctx, Job *j, int64_t first, int64_t count, const double 
     const int64_t grid = (count + SIM_THREADS - 1) / SIM_THREADS;
     if (ctx->exact_poisson) vx_sim_kernel<SIM_DUMP, 1><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
     else if (latency) vx_sim_kernel<SIM_DUMP, 0, 1><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
-    else vx_sim_kernel<SIM_DUMP, 0><<<(unsigned)grid, SIM_THREADS, 0, st>>>(a);
+    else vx_sim_kernel<SIM_DUMP, 0><<<(unsigned)grid, SIM_THREADS, pad_smem, st>>>(a);
     CKL();
     return VX_OK;
 }
@@ -765,15 +769,17 @@ static int create_ctx(vx_ctx **out, int device, bool side_high_priority)
     c->device = device;
     c->trace = getenv("VX_TRACE") != nullptr;
     cudaError_t e = cudaSetDevice(device);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) {
-        // a grid sub-context runs its box's pilot on the side stream, which then outranks the main
-        // streams: the pilot is short and gates a long fold, other boxes' folds should not delay it
-        int lo_pri = 0, hi_pri = 0;
-        cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
-        e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_high_priority ? hi_pri : lo_pri);
-    }
+    int lo_pri = 0, hi_pri = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+    // a grid sub-context runs its box's pilot on the side stream, which then outranks the main
+    // streams: the pilot is short and gates a long fold, other boxes' folds should not delay it.
+    // A whole-job context is the other way round: pilot and fold stepper on the main stream outrank
+    // the filler work (side DUMP, matrix folds) of the side stream.
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, side_high_priority ? lo_pri : hi_pri);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, side_high_priority ? hi_pri : lo_pri);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sorted, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_wins, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int sm = 0;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
@@ -798,6 +804,8 @@ void vx_destroy(vx_ctx *ctx)
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->side) cudaStreamDestroy(ctx->side);
     if (ctx->side_done) cudaEventDestroy(ctx->side_done);
+    if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
+    if (ctx->ev_wins) cudaEventDestroy(ctx->ev_wins);
     delete ctx;
 }
 
@@ -825,6 +833,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "fold_pad_smem") ctx->fold_pad_smem = (int64_t)value;
     else if (s == "exact_poisson") ctx->exact_poisson = value != 0;
     else if (s == "side_samples") ctx->side_samples = (int64_t)value;
+    else if (s == "side_pad_smem") ctx->side_pad_smem = (int64_t)value;
     else if (s == "select_global") ctx->select_global = value != 0;
     else if (s == "pipe_pilot") ctx->pipe_pilot = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
@@ -989,40 +998,6 @@ static int pilot_launch(vx_ctx *ctx, bool on_side)
     const int64_t np = j->direct ? n : std::min(n, j->cfg.pilot_samples > 0 ? j->cfg.pilot_samples
                                                      : default_pilot(j->cfg.q_lo, j->cfg.q_hi, std::max<int64_t>(n / j->world, 1)));
     j->n_pilot = np;
-    if (!j->direct && !(j->cfg.max_running_time > 0.0)) {
-        // the part of the shard the stepper will fold (the pilot's own samples come from its matrix)
-        int64_t lo = std::max(j->shard_first, np);
-        const int64_t hi = j->shard_first + j->shard_count;
-        // (a) its first `side` samples are stepped NOW by a DUMP launch on the side stream: the
-        //     pilot stepper is one serial T-day chain on < 1 CTA per SM, so the GPU is > 85 % idle
-        //     until the windows exist; those rows are folded from their matrix afterwards
-        //     (default 2 x the pilot: measured on B200 at 1e6 samples, 0 / 32768 / 65536 / 131072 side
-        //     samples give 4.49 / 4.43 / 4.46 / 4.59 ms per job -- warps co-resident with the pilot's
-        //     slow its serial chain, so only a thin layer of extra work is free)
-        int64_t side = ctx->side_samples >= 0 ? ctx->side_samples : std::min<int64_t>(2 * np, (int64_t)1 << 18);
-        if (on_side) side = 0;
-        side = std::min(side, hi - lo);
-        if (side * 4 > hi - lo) side = (hi - lo >= 4096) ? (hi - lo) / 4 : 0;   // never more than a quarter of the shard
-        side &= ~(int64_t)127;
-        if ((double)R * (double)side * 4.0 > 16e9) side = 0;
-        if (side > 0) {
-            void *p_ = nullptr;
-            rc = pool_get(ctx, SLOT_SIDE, sizeof(int32_t) * R * side, &p_);
-            if (rc) return rc;
-            j->d_side = (int32_t *)p_;
-            j->side_first = lo; j->side_count = side;
-            rc = launch_dump(ctx, j, lo, side, j->d_params ? j->d_params + 6 * lo : nullptr, j->d_side, side, ctx->side);
-            if (rc) return rc;
-            lo += side;
-        }
-        // (b) the rest is counting-sorted by pressure bucket (regime sort), also on the side stream
-        if (ctx->sort_samples && !j->explicit_params && hi - lo >= 4096 && hi - lo <= ((int64_t)1 << 30)) {
-            rc = launch_regime_sort(ctx, j, lo, hi - lo, ctx->side, &j->d_perm);
-            if (rc) return rc;
-            j->perm_first = lo; j->perm_count = hi - lo;
-        }
-        if (!on_side) CK(cudaEventRecord(ctx->side_done, ctx->side));
-    }
     if ((double)R * (double)np * 4.0 > 120e9) return fail(ctx, VX_ERR_NOMEM, "direct/pilot matrix too large");
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_DUMP, sizeof(int32_t) * R * np, &p_); if (rc_) return rc_; j->d_dump = (int32_t *)p_; }
     rc = launch_dump(ctx, j, 0, np, j->d_params, j->d_dump, np, ps);
@@ -1049,6 +1024,46 @@ static int pilot_launch(vx_ctx *ctx, bool on_side)
     rc = select_launch(ctx, j->d_dump, R, np, np, ranks, ps);
     if (rc) return rc;
     CK(cudaEventRecord(j->evB, ps));
+    // Everything below is queued BEHIND the pilot (host order): its few CTAs must be resident before
+    // the side stream's launches fill the SMs.
+    if (!j->direct && !(j->cfg.max_running_time > 0.0)) {
+        // the part of the shard the stepper will fold (the pilot's own samples come from its matrix)
+        int64_t lo = std::max(j->shard_first, np);
+        const int64_t hi = j->shard_first + j->shard_count;
+        // (a) optionally its first `side` samples are stepped NOW by a DUMP launch on the
+        //     (low-priority) side stream and folded from their matrix later (vx_fold_matrix_kernel):
+        //     the pilot stepper is one serial T-day chain on < 1 CTA per SM, followed by a select and a
+        //     host round trip, ~0.5 ms during which the GPU is > 85 % idle.  Measured on B200 (1e6
+        //     samples, ms per job for 0 / 32768 / 65536 / 98304 / 131072 side samples): 4.00 / 4.01 /
+        //     4.01 / 4.05 / 4.10 -- every co-resident warp slows the pilot's chain and delays its
+        //     select by as much as the fold saves, also when the pilot's CTAs are packed onto SMs of
+        //     their own (512-thread CTAs holding all the shared memory: 4.09 at 118784).  So the
+        //     default is none; "side_samples" keeps the path for other shapes.
+        int64_t side = ctx->side_samples >= 0 ? ctx->side_samples : 0;
+        if (on_side) side = 0;
+        side = std::min(side, hi - lo);
+        if (side * 4 > hi - lo) side = (hi - lo >= 4096) ? (hi - lo) / 4 : 0;   // never more than a quarter of the shard
+        side &= ~(int64_t)127;
+        if ((double)R * (double)side * 4.0 > 16e9) side = 0;
+        // (b) the rest is counting-sorted by pressure bucket (regime sort), first thing on the side
+        //     stream: the fold needs the order as soon as the windows exist
+        if (ctx->sort_samples && !j->explicit_params && hi - (lo + side) >= 4096 && hi - (lo + side) <= ((int64_t)1 << 30)) {
+            rc = launch_regime_sort(ctx, j, lo + side, hi - (lo + side), ctx->side, &j->d_perm);
+            if (rc) return rc;
+            j->perm_first = lo + side; j->perm_count = hi - (lo + side);
+            if (!on_side) CK(cudaEventRecord(ctx->ev_sorted, ctx->side));
+        }
+        if (side > 0) {
+            void *p_ = nullptr;
+            rc = pool_get(ctx, SLOT_SIDE, sizeof(int32_t) * R * side, &p_);
+            if (rc) return rc;
+            j->d_side = (int32_t *)p_;
+            j->side_first = lo; j->side_count = side;
+            rc = launch_dump(ctx, j, lo, side, j->d_params ? j->d_params + 6 * lo : nullptr, j->d_side, side, ctx->side,
+                             nullptr, (size_t)ctx->side_pad_smem);
+            if (rc) return rc;
+        }
+    }
     if (on_side) CK(cudaEventRecord(ctx->side_done, ctx->side));
     j->pilot_stage = 2;
     return VX_OK;
@@ -1135,23 +1150,43 @@ static int accumulate_impl(vx_ctx *ctx, bool sync_end)
     const int64_t todo = first_pass ? j->shard_count : j->shard_done;
     const bool timed = first_pass && j->cfg.max_running_time > 0.0;
     const int64_t chunk = timed ? ctx->chunk_samples : ((int64_t)1 << 30);
-    if (j->d_side || j->d_perm) CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));
-    CK(cudaEventRecord(j->evA, ctx->stream));
-    // samples of this shard that the pilot already simulated: fold its matrix, not a re-run
+    // Samples that already exist as raw rows -- the pilot's share of this shard and the samples
+    // stepped beside the pilot -- are folded from their matrices.  With a side stream of its own (a
+    // whole job, not a grid sub-context whose side stream carries the pilot) that HBM-streaming work
+    // runs BESIDE the issue-bound stepper below: the side stream has the lower priority, so its CTAs
+    // fill the SMs the stepper's tail leaves idle.
+    const bool matrix_on_side = j->pilot_stream != ctx->side && !timed;
+    cudaStream_t ms = matrix_on_side ? ctx->side : ctx->stream;
+    if (matrix_on_side) {
+        CK(cudaEventRecord(ctx->ev_wins, ctx->stream));          // window table uploaded, slab cleared
+        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_wins, 0));
+    } else if (j->d_side || j->d_perm) {
+        CK(cudaEventRecord(ctx->side_done, ctx->side));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));
+    }
     const int64_t lo = j->shard_first, hi = j->shard_first + todo;
     const int64_t pil_hi = (j->d_dump && j->n_pilot > 0) ? std::min(hi, j->n_pilot) : lo;
     int64_t done = 0;
+    auto fold_matrix = [&](const int32_t *d, int64_t ld, int64_t c0, int64_t c1) {
+        const int64_t chunks = (c1 - c0 + FM_COLS - 1) / FM_COLS;
+        const dim3 grid((unsigned)j->R, (unsigned)std::min<int64_t>(chunks, 4096));
+        vx_fold_matrix_kernel<<<grid, FM_THREADS, 0, ms>>>(d, ld, c0, c1, j->d_wins, j->d_acc, (int)j->R, j->bins64);
+    };
     if (pil_hi > lo) {
-        vx_fold_matrix_kernel<<<(unsigned)j->R, 256, 0, ctx->stream>>>(j->d_dump, j->n_pilot, lo, pil_hi, j->d_wins, j->d_acc, (int)j->R, j->bins64);
+        fold_matrix(j->d_dump, j->n_pilot, lo, pil_hi);
         CKL();
         done = pil_hi - lo;
     }
-    // ... and the samples stepped on the side stream while the pilot ran
     if (j->d_side && j->side_count > 0 && j->side_first == j->shard_first + done) {
-        vx_fold_matrix_kernel<<<(unsigned)j->R, 256, 0, ctx->stream>>>(j->d_side, j->side_count, 0, j->side_count, j->d_wins, j->d_acc, (int)j->R, j->bins64);
+        fold_matrix(j->d_side, j->side_count, 0, j->side_count);
         CKL();
         done += j->side_count;
     }
+    if (matrix_on_side) {
+        CK(cudaEventRecord(ctx->side_done, ctx->side));
+        if (j->d_perm && first_pass) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sorted, 0));
+    }
+    CK(cudaEventRecord(j->evA, ctx->stream));
     int64_t stepped = 0;
     auto out_of_time = [&]() {       // model.py:187-189, at chunk granularity; something is always folded first
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - j->t_begin).count() > j->cfg.max_running_time;
@@ -1186,6 +1221,7 @@ static int accumulate_impl(vx_ctx *ctx, bool sync_end)
     j->n_passes++;
     CK(cudaEventRecord(j->evB, ctx->stream));
     j->fold_timing_pending = true;
+    if (matrix_on_side) CK(cudaStreamWaitEvent(ctx->stream, ctx->side_done, 0));   // the matrices' share of the slab
     if (j->use_comm && ctx->comm) {
         // the path's one exchange step: all-reduce(sum) of the integer slab, issued on the stream the
         // fold ran on, so it starts the moment this rank's last fold CTA retires

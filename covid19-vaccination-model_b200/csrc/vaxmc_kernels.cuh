@@ -749,20 +749,26 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
         atomicAdd(a.acc + 0, (unsigned long long)nvalid);  // header word 0: samples folded
 }
 
-// Fold of an already materialised block of raw rows (the pilot matrix) into the accumulator
-// slab: same sums / counts-below / window histograms as the FOLD stepper produces, so the
-// pilot samples are not simulated twice.  One CTA per row, columns [c0, c1).
-__global__ void __launch_bounds__(256) vx_fold_matrix_kernel(const int32_t *__restrict__ dump,
-                                                             int64_t ld, int64_t c0, int64_t c1,
-                                                             const Win *__restrict__ wins,
-                                                             unsigned long long *acc, int R, int bins64)
+// Fold of an already materialised block of raw rows (the pilot matrix, and the samples stepped
+// beside the pilot) into the accumulator slab: same sums / counts-below / window histograms as the
+// FOLD stepper produces, so those samples are not simulated twice.  HBM-streaming: grid =
+// (row, column chunk), every thread has its FM_VEC 16-byte loads in flight before it touches a
+// value; the launch runs on the low-priority side stream beside the issue-bound fold stepper (the
+// slab only ever sees integer atomics, so the two commute).
+constexpr int FM_THREADS = 256, FM_VEC = 8, FM_COLS = FM_THREADS * FM_VEC * 4;   // 8192 columns per CTA
+
+__global__ void __launch_bounds__(FM_THREADS) vx_fold_matrix_kernel(const int32_t *__restrict__ dump,
+                                                                    int64_t ld, int64_t c0, int64_t c1,
+                                                                    const Win *__restrict__ wins,
+                                                                    unsigned long long *acc, int R, int bins64)
 {
-    __shared__ unsigned long long sh[3][256];
+    __shared__ unsigned long long sh[3][FM_THREADS / 32];
     const int row = blockIdx.x;
     const Win wl = wins[row * 2], wh = wins[row * 2 + 1];
     unsigned long long *hist = acc + ACC_HDR + 3 * (int64_t)R;
     const int32_t *src = dump + (int64_t)row * ld;
-    unsigned long long sum = 0, clo = 0, chi = 0;
+    unsigned long long sum = 0;
+    uint32_t clo = 0, chi = 0;
     auto one = [&](const int v) {
         sum += (unsigned long long)(uint32_t)v;
         const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
@@ -770,32 +776,37 @@ __global__ void __launch_bounds__(256) vx_fold_matrix_kernel(const int32_t *__re
         if (dl < wl.len) bin_add(hist, wl.off + (dl >> wl.shift), bins64);
         if (dh < wh.len) bin_add(hist, wh.off + (dh >> wh.shift), bins64);
     };
-    // 16-byte loads, two in flight per thread (HBM/L2 streaming: this kernel only reads)
-    int64_t c = c0;
-    if (((ld | c0) & 3) == 0) {
-        const int4 *src4 = reinterpret_cast<const int4 *>(src + c0);
-        const int64_t n4 = (c1 - c0) / 4;
-        int64_t i = threadIdx.x;
-        for (; i + 256 < n4; i += 512) {
-            const int4 a = src4[i], b = src4[i + 256];
-            one(a.x); one(a.y); one(a.z); one(a.w); one(b.x); one(b.y); one(b.z); one(b.w);
+    const bool aligned = ((ld | c0) & 3) == 0;
+    for (int64_t cb = c0 + (int64_t)blockIdx.y * FM_COLS; cb < c1; cb += (int64_t)gridDim.y * FM_COLS) {
+        const int64_t ce = min(c1, cb + FM_COLS);
+        if (aligned && ce - cb == FM_COLS) {
+            const int4 *src4 = reinterpret_cast<const int4 *>(src + cb) + threadIdx.x;
+            int4 v[FM_VEC];
+#pragma unroll
+            for (int k = 0; k < FM_VEC; ++k) v[k] = src4[k * FM_THREADS];
+#pragma unroll
+            for (int k = 0; k < FM_VEC; ++k) { one(v[k].x); one(v[k].y); one(v[k].z); one(v[k].w); }
+        } else {
+            for (int64_t c = cb + threadIdx.x; c < ce; c += FM_THREADS) one(src[c]);
         }
-        for (; i < n4; i += 256) { const int4 a = src4[i]; one(a.x); one(a.y); one(a.z); one(a.w); }
-        c = c0 + 4 * n4;
     }
-    for (c += threadIdx.x; c < c1; c += 256) one(src[c]);
-    sh[0][threadIdx.x] = sum; sh[1][threadIdx.x] = clo; sh[2][threadIdx.x] = chi;
+    unsigned long long lo64 = clo, hi64 = chi;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        lo64 += __shfl_xor_sync(0xffffffffu, lo64, o);
+        hi64 += __shfl_xor_sync(0xffffffffu, hi64, o);
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { sh[0][wid] = sum; sh[1][wid] = lo64; sh[2][wid] = hi64; }
     __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off)
-            for (int k = 0; k < 3; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + off];
-        __syncthreads();
-    }
     if (threadIdx.x == 0) {
-        atomicAdd(acc + ACC_HDR + row, sh[0][0]);
-        if (sh[1][0]) atomicAdd(acc + ACC_HDR + R + 2 * row, sh[1][0]);
-        if (sh[2][0]) atomicAdd(acc + ACC_HDR + R + 2 * row + 1, sh[2][0]);
-        if (row == 0) atomicAdd(acc + 0, (unsigned long long)(c1 - c0));
+        unsigned long long t[3] = {0, 0, 0};
+        for (int w = 0; w < FM_THREADS / 32; ++w) { t[0] += sh[0][w]; t[1] += sh[1][w]; t[2] += sh[2][w]; }
+        atomicAdd(acc + ACC_HDR + row, t[0]);
+        if (t[1]) atomicAdd(acc + ACC_HDR + R + 2 * row, t[1]);
+        if (t[2]) atomicAdd(acc + ACC_HDR + R + 2 * row + 1, t[2]);
+        if (row == 0 && blockIdx.y == 0) atomicAdd(acc + 0, (unsigned long long)(c1 - c0));
     }
 }
 

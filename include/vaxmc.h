@@ -126,7 +126,7 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * (granularity of the max_running_time check, default 2^20), "exact_poisson" (1: validation
  * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; ~11x slower),
  * "side_samples" (samples stepped on a side stream while the pilot runs and folded from their
- * matrix; -1 = default 2 x pilot, 0 = none; same integers either way).                       */
+ * matrix; default 0 = none -- measured neutral on B200; same integers either way).            */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
  * vx_trim returns it to the driver. */

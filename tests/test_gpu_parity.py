@@ -511,7 +511,7 @@ def test_streamed_refinement_paths(vax, ctx):
     finally:
         ctx.set_option("side_samples", -1); ctx.set_option("max_bins", 262144)
     dflt = _run(vax, ctx, bounds, 200_000, 6, direct_max=1)
-    assert dflt.c.side_samples > 0 and dflt.c.n_pilot == 16384
+    assert dflt.c.side_samples == 0 and dflt.c.n_pilot == 16384     # default: nothing stepped beside the pilot
     assert dflt.c.fold_samples == 200_000 - dflt.c.n_pilot - dflt.c.side_samples
     assert _same(dflt, _run(vax, ctx, bounds, 200_000, 6, direct_max=1 << 20))
     # single-value bounds ([v, v], model.py:376-377): every sample has the same tuple
