@@ -182,7 +182,7 @@ struct vx_ctx {
     int64_t fold_pad_smem = 0;            // experiment knob: unused dynamic smem to lower occupancy
     int64_t exact_poisson = 0;            // validation mode: inversion < 10, PTRS above (see kernels)
     int64_t pipe_pilot = 1;               // latency variant of the stepper for launches that cannot fill the GPU
-    int64_t select_global = 0;            // 1: always the global-memory radix select (tests: both kernels, same answers)
+    int64_t select_global = 0;            // 1: the 8-bit radix select, 2: the streamed histogram select, whatever the row length (tests: same answers)
     int64_t side_samples = -1;            // samples stepped beside the pilot (-1 = default = 0: none, see pilot_launch)
     int64_t side_pad_smem = 0;            // experiment knob: dynamic smem of the side DUMP launch (limits its CTAs per SM)
     int sm_count = 148;
@@ -537,19 +537,23 @@ int select_launch(vx_ctx *ctx, const int32_t *d_data, int64_t rows, int64_t ld, 
       rc_ = pool_get(ctx, SLOT_SEL_SUMS, sizeof(long long) * rows, &p_); if (rc_) return rc_; d_sums = (long long *)p_;
       rc_ = hpin_get(ctx, HSLOT_SEL, sizeof(long long) * rows + sizeof(int32_t) * rows * K, &h); if (rc_) return rc_; }
     CK(cudaMemcpyAsync(d_ranks, ranks.data(), sizeof(int64_t) * K, cudaMemcpyHostToDevice, st));
-    // rows that fit in shared memory (the pilot: 64 KB per row) are selected on chip after one read
+    // histogram-refinement select: rows that fit in shared memory (the pilot: 64 KB per row) are
+    // staged and selected on chip after one read, longer rows are streamed once per pass;
+    // "select_global" = 1 forces the 8-bit radix kernel (cross-check), 2 the streamed variant
     const size_t smem = sizeof(int32_t) * (size_t)((n + 3) & ~(int64_t)3) + sizeof(uint32_t) * SELS_BINS;
-    if (smem <= 200 * 1024 && !ctx->select_global) {
+    if (ctx->select_global == 1) {
+        vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
+    } else if (smem <= 200 * 1024 && ctx->select_global == 0) {
         static bool attr_set[64] = {false};
         if (ctx->device < 64 && !attr_set[ctx->device]) {
-            CK(cudaFuncSetAttribute(vx_select_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            CK(cudaFuncSetAttribute(vx_select_hist_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             // all of the SM's L1/shared array as shared memory: two 80 KB rows resident per SM
-            CK(cudaFuncSetAttribute(vx_select_smem_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            CK(cudaFuncSetAttribute(vx_select_hist_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             attr_set[ctx->device] = true;
         }
-        vx_select_smem_kernel<<<(unsigned)rows, SELS_THREADS, smem, st>>>(d_data, ld, (int)n, d_ranks, K, d_out, d_sums);
+        vx_select_hist_kernel<true><<<(unsigned)rows, SELS_THREADS, smem, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
     } else {
-        vx_select_kernel<int32_t><<<(unsigned)rows, SEL_THREADS, 0, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
+        vx_select_hist_kernel<false><<<(unsigned)rows, SELS_THREADS, sizeof(uint32_t) * SELS_BINS, st>>>(d_data, ld, n, d_ranks, K, d_out, d_sums);
     }
     CKL();
     CK(cudaMemcpyAsync(h, d_sums, sizeof(long long) * rows, cudaMemcpyDeviceToHost, st));
@@ -834,7 +838,7 @@ int vx_set_option(vx_ctx *ctx, const char *name, double value)
     else if (s == "exact_poisson") ctx->exact_poisson = value != 0;
     else if (s == "side_samples") ctx->side_samples = (int64_t)value;
     else if (s == "side_pad_smem") ctx->side_pad_smem = (int64_t)value;
-    else if (s == "select_global") ctx->select_global = value != 0;
+    else if (s == "select_global") ctx->select_global = (int64_t)value;
     else if (s == "pipe_pilot") ctx->pipe_pilot = value != 0;
     else return fail(ctx, VX_ERR_ARG, "unknown option %s", name);
     return VX_OK;

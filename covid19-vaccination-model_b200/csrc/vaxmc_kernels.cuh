@@ -728,6 +728,31 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
                         hit(v);
                     }
                 }
+#ifndef VX_HITS_PER_QUAD
+                if (__popc(hits) >= 16) {
+                    // a row whose samples (almost) all sit in a window is a flat or nearly flat row --
+                    // single-value bounds make the delivery rows deterministic, for one: run-length
+                    // aggregate the bins, or 32 atomics per warp and tile would queue on one address
+                    uint32_t pl = 0, ph = 0, nl = 0, nh = 0;
+                    while (hits) {
+                        const int v = row[__ffs((int)hits) - 1];
+                        hits &= hits - 1;
+                        const uint32_t dl = (uint32_t)(v - wl.a), dh = (uint32_t)(v - wh.a);
+                        if (dl < wl.len) {
+                            const uint32_t b = wl.off + (dl >> wl.shift);
+                            if (nl && b != pl) { bin_add(hist, pl, a.bins64, nl); nl = 0; }
+                            pl = b; ++nl;
+                        }
+                        if (dh < wh.len) {
+                            const uint32_t b = wh.off + (dh >> wh.shift);
+                            if (nh && b != ph) { bin_add(hist, ph, a.bins64, nh); nh = 0; }
+                            ph = b; ++nh;
+                        }
+                    }
+                    if (nl) bin_add(hist, pl, a.bins64, nl);
+                    if (nh) bin_add(hist, ph, a.bins64, nh);
+                }
+#endif
                 while (hits) {
                     const int sidx = __ffs((int)hits) - 1;
                     hits &= hits - 1;
@@ -1048,23 +1073,28 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
     if (tid < nranks) out[(int64_t)blockIdx.x * nranks + tid] = KT::from_key(S.prefix[tid]);
 }
 
-// The same order statistics for rows that fit in shared memory (the pilot matrix: 16384 columns =
-// 64 KB per row).  The row is read from HBM/L2 ONCE into shared memory (row sum, min and max on the
-// way), then located by histogram refinement entirely on chip: 4096 bins over [min, max] first,
-// then, if a bin is wider than one value, all still-open ranks at once with 4096 / #ranks bins
-// each over their bins -- two levels resolve a range of 2^22+, three any int32 row.  ~6
-// instructions per element and level against ~25 per element and 8-bit digit of the
-// global-memory kernel above, which stays for rows that do not fit.
+// Order statistics of int32 rows by histogram refinement (the default for int32; the radix kernel
+// above stays for fp64 rows and as a cross-check).  One CTA per row:
+//   pass 0   row sum, min and max (the only pass that looks at every bit of every value)
+//   level 0  4096 bins over [min, max]
+//   level k  all still-open ranks at once, 4096 / #ranks bins each over their bins --
+//            two levels resolve a range of 2^22+, three any int32 row.
+// STAGED: the row fits in shared memory (the pilot matrix: 16384 columns = 64 KB per row): it is
+//         read from HBM/L2 ONCE and the levels run on chip.
+// else:   the row is streamed from global memory once per pass with 16-byte loads (1 + levels
+//         reads, typically 3, ~6 instructions per element and pass; the 8-bit radix select needs
+//         1 + 4 reads at ~25 instructions per element and pass).
 constexpr int SELS_THREADS = 512;
 constexpr int SELS_BINS = 4096;
 
-__global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_smem_kernel(
-    const int32_t *__restrict__ data, int64_t ld, int n, const int64_t *__restrict__ ranks, int nranks,
+template <bool STAGED>
+__global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_hist_kernel(
+    const int32_t *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks, int nranks,
     int32_t *__restrict__ out /*[rows][nranks]*/, long long *__restrict__ sums /*[rows]*/)
 {
     extern __shared__ __align__(16) int sels_sm[];
-    int *vals = sels_sm;                                            // [n rounded up to 4]
-    uint32_t *hist = reinterpret_cast<uint32_t *>(sels_sm + ((n + 3) & ~3));   // [SELS_BINS]
+    int *vals = sels_sm;                                            // STAGED: [n rounded up to 4]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(sels_sm + (STAGED ? (int)((n + 3) & ~(int64_t)3) : 0));   // [SELS_BINS]
     __shared__ long long red_sum[SELS_THREADS / 32];
     __shared__ int red_min[SELS_THREADS / 32], red_max[SELS_THREADS / 32];
     __shared__ uint32_t warp_tot[SELS_THREADS / 32];
@@ -1076,23 +1106,60 @@ __global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_smem_kernel(
     __shared__ uint32_t slot_base[SEL_MAXR];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int32_t *row = data + (int64_t)blockIdx.x * ld;
+    const bool vec = ((ld | n) & 3) == 0;
+    const int64_t n4 = n / 4;
 
-    // ---- stage the row; sum / min / max
+    // Every value of the row, four per thread and step where the layout allows, with a uniform trip
+    // count (f may use warp collectives); `ok` is false for the padding of the last step.
+    auto for_each4 = [&](auto &&f) {
+        if (vec) {
+            const int4 *src = STAGED ? reinterpret_cast<const int4 *>(vals) : reinterpret_cast<const int4 *>(row);
+            int64_t i0 = 0;
+            if (!STAGED)       // two 16-byte loads in flight per thread
+                for (; i0 + 2 * SELS_THREADS <= n4; i0 += 2 * SELS_THREADS) {
+                    const int4 a = src[i0 + tid], b = src[i0 + SELS_THREADS + tid];
+                    f(a, true); f(b, true);
+                }
+            for (; i0 < n4; i0 += SELS_THREADS) {
+                const bool ok = i0 + tid < n4;
+                const int4 a = ok ? src[i0 + tid] : make_int4(0, 0, 0, 0);
+                f(a, ok);
+            }
+        } else {
+            const int32_t *src = STAGED ? vals : row;
+            for (int64_t i0 = 0; i0 < n; i0 += SELS_THREADS) {
+                const bool ok = i0 + tid < n;
+                const int v = ok ? src[i0 + tid] : 0;
+                f(make_int4(v, v, v, v), ok, 1);
+            }
+        }
+    };
+
+    // ---- pass 0: (stage the row;) sum / min / max
     long long acc = 0;
     int mn = INT_MAX, mx = INT_MIN;
-    if (((ld | (int64_t)n) & 3) == 0) {
+    if (vec) {
         const int4 *src = reinterpret_cast<const int4 *>(row);
-        for (int i = tid; i < n / 4; i += SELS_THREADS) {
+        int64_t i = tid;
+        if (!STAGED)
+            for (; i + SELS_THREADS < n4; i += 2 * SELS_THREADS) {
+                const int4 v = src[i], w = src[i + SELS_THREADS];
+                acc += (long long)v.x + v.y + v.z + v.w + w.x + w.y + w.z + w.w;
+                mn = min(min(min(mn, v.x), min(v.y, min(v.z, v.w))), min(min(w.x, w.y), min(w.z, w.w)));
+                mx = max(max(max(mx, v.x), max(v.y, max(v.z, v.w))), max(max(w.x, w.y), max(w.z, w.w)));
+            }
+        for (; i < n4; i += SELS_THREADS) {
             const int4 v = src[i];
-            reinterpret_cast<int4 *>(vals)[i] = v;
+            if (STAGED) reinterpret_cast<int4 *>(vals)[i] = v;
             acc += (long long)v.x + v.y + v.z + v.w;
             mn = min(min(mn, v.x), min(v.y, min(v.z, v.w)));
             mx = max(max(mx, v.x), max(v.y, max(v.z, v.w)));
         }
     } else {
-        for (int i = tid; i < n; i += SELS_THREADS) {
+        for (int64_t i = tid; i < n; i += SELS_THREADS) {
             const int v = row[i];
-            vals[i] = v; acc += v; mn = min(mn, v); mx = max(mx, v);
+            if (STAGED) vals[i] = v;
+            acc += v; mn = min(mn, v); mx = max(mx, v);
         }
     }
 #pragma unroll
@@ -1145,11 +1212,9 @@ __global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_smem_kernel(
         if (nd == 1) {
             const long long lo = s_lo[0], w = s_w[0];
             const int sh = s_shift[0];
-            for (int i0 = 0; i0 < n; i0 += SELS_THREADS) {
-                const int i = i0 + tid;
-                const bool in = i < n;
-                const long long d = in ? (long long)vals[i] - lo : -1;
-                const bool hit = in && d >= 0 && d < w;
+            auto one = [&](const int v, const bool ok) {
+                const long long d = ok ? (long long)v - lo : -1;
+                const bool hit = ok && d >= 0 && d < w;
                 const uint32_t b = hit ? (uint32_t)(d >> sh) : 0xffffffffu;
                 // flat rows: the whole warp in one bin -> one atomic instead of 32 serialised ones
                 const uint32_t b0 = __shfl_sync(0xffffffffu, b, 0);
@@ -1158,15 +1223,24 @@ __global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_smem_kernel(
                 } else if (hit) {
                     atomicAdd(&hist[b], 1u);
                 }
-            }
+            };
+            for_each4([&](const int4 v, const bool ok, const int cnt = 4) {
+                one(v.x, ok);
+                if (cnt == 4) { one(v.y, ok); one(v.z, ok); one(v.w, ok); }
+            });
         } else {
-            for (int i = tid; i < n; i += SELS_THREADS) {
-                const long long v = vals[i];
+            auto one = [&](const int vi) {
+                const long long v = vi;
                 for (int d = 0; d < nd; ++d) {
                     const long long dd = v - s_lo[d];
                     if (dd >= 0 && dd < s_w[d]) { atomicAdd(&hist[d * per + (int)(dd >> s_shift[d])], 1u); break; }
                 }
-            }
+            };
+            for_each4([&](const int4 v, const bool ok, const int cnt = 4) {
+                if (!ok) return;
+                one(v.x);
+                if (cnt == 4) { one(v.y); one(v.z); one(v.w); }
+            });
         }
         __syncthreads();
         // ---- exclusive scan of the SELS_BINS counts (8 per thread), restarted at every interval's first bin

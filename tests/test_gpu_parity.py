@@ -133,10 +133,11 @@ def test_radix_select_exact(ctx):
         rk = sorted({0, m // 2, m - 1})
         got, sums = ctx.test_select(d, rk)
         assert np.array_equal(got, np.sort(d, axis=1)[:, rk]), m
-    # the two kernels (rows staged in shared memory up to ~47k columns; radix passes over global
-    # memory above) on the same data: wide ranges (three histogram levels), negatives, int32 extremes,
-    # duplicate ranks, odd row lengths (unaligned rows take the scalar load path)
-    for n in (16384, 16383, 47000, 47104, 1000):
+    # the three kernels (histogram refinement with the row staged in shared memory up to ~47k columns
+    # or streamed from global memory above; 8-bit radix passes as the cross-check) on the same data:
+    # wide ranges (three histogram levels), negatives, int32 extremes, duplicate ranks, odd row
+    # lengths (unaligned rows take the scalar load path), rows longer than two load steps
+    for n in (16384, 16383, 47000, 47104, 1000, 5000, 200000, 200003):
         data = np.stack([
             rng.integers(-(1 << 31), (1 << 31) - 1, n), rng.integers(0, 1 << 27, n), rng.integers(-5, 5, n),
             np.full(n, -(1 << 31)), np.full(n, (1 << 31) - 1), rng.poisson(40, n), rng.poisson(3e5, n),
@@ -147,7 +148,7 @@ def test_radix_select_exact(ctx):
         want = np.sort(data, axis=1)[:, ranks]
         try:
             outs = []
-            for g in (0, 1):
+            for g in (0, 1, 2):
                 ctx.set_option("select_global", g)
                 got, sums = ctx.test_select(data, ranks)
                 assert np.array_equal(got, want), (n, g)
