@@ -163,8 +163,12 @@ __device__ __forceinline__ float normal_cdf(float z)
 //                        values are a=(.01725,-.00352,-.00133), b=(-.0015,-.0113,.0013,.0006));
 //                        oracle/fit_poisson_cf.py regenerates them and prints the resulting
 //                        sup-CDF error against the exact law: <=1.5e-4 on [2,3], 6.4e-5 at 3.5,
-//                        <=4.8e-5 for lam>=4, <=1.5e-5 for lam>=10, <2e-6 for lam>=32
-//                        (tests/test_sampler_math.py pins these).  The threshold is where
+//                        <=4.8e-5 for lam>=4, <=1.5e-5 for lam>=10, <2e-6 for lam>=32, and the
+//                        bias of the first two moments: |E X - lam| <= 1.2e-4 counts (7.4e-5 sd),
+//                        |Var X / lam - 1| <= 3e-4 (tests/test_sampler_math.py pins these; a
+//                        refit that weights the moments buys a 5x smaller bias with 30-130 %
+//                        relative errors in the far tail at lam ~ 2, so it was not adopted --
+//                        see the script).  The threshold is where
 //                        the divergent inversion loop stops paying: at 10 (numpy's) it was
 //                        43 % of all issued instructions, at 4 it was 10 %, at 2 it is 4 %.
 constexpr float POISSON_INV_MAX = 2.0f;

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 import philox_ref as pr
-from fit_poisson_cf import law_error, q5
+from fit_poisson_cf import law_error, moment_bias, q5
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CUH = os.path.join(ROOT, "covid19-vaccination-model_b200", "csrc", "vaxmc_kernels.cuh")
@@ -54,6 +54,19 @@ def test_poisson_expansion_error_bounds():
         sup, chi = law_error(lam, lambda z, l: q5(z, l, a, b), M=1_000_001)
         assert sup <= bound, (lam, sup)
         assert chi <= 8e-7 or lam > 1000, (lam, chi)        # needs > 2e7 draws at ONE lam to show at 3 sigma
+
+
+def test_poisson_expansion_moment_bias():
+    """What a 1e9-sample job can see of the approximate sampler: the bias of its first two moments
+    (DESIGN.md 3.1 quotes these; profiles/r02_sampler_bias_1e9.jsonl is the measurement)."""
+    a = [_const("CF_A1"), _const("CF_A3"), _const("CF_A5")]
+    b = [_const("CF_B0"), _const("CF_B2"), _const("CF_B4"), _const("CF_B6")]
+    for lam in (2, 2.5, 3, 4, 6, 8, 10, 16, 32, 100):
+        dm, dv = moment_bias(lam, lambda z, l: q5(z, l, a, b))
+        assert abs(dm) <= 1.25e-4 and abs(dm) / np.sqrt(lam) <= 8e-5, (lam, dm)
+        assert abs(dv) / lam <= 3.2e-4, (lam, dv)
+        if lam >= 32:
+            assert abs(dm) <= 1.2e-5, (lam, dm)
 
 
 def test_inversion_regime_tail_is_negligible():

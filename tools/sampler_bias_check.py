@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
+    only = sys.argv[2] if len(sys.argv) > 2 else ""          # substring of the scenario name
     vax = importlib.import_module("covid19-vaccination-model_b200")
     nat = vax._native
     ctx = vax.default_context(0)
@@ -28,6 +29,8 @@ def main():
                       ("strong pressure", (0.30, 0.055, 0.1, 4.0, 0.009, 0.125)),
                       # the README USA box itself (mixed parameters): here sd is the spread across samples
                       ("USA bounds", (0.35, 0.45, 0.12, 0.25, 0.0, 0.02, 5, 7, 0.01, 0.012, 0.05, 0.10))):
+        if only and only not in name:
+            continue
         b = np.array(tup) if len(tup) == 12 else np.repeat(np.array(tup), 2)
         res = {}
         for exact in (0, 1):
