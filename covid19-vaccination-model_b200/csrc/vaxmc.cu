@@ -132,6 +132,7 @@ struct Job {
     int32_t *d_side = nullptr;
     int64_t side_first = 0, side_count = 0;
     bool stats_on_device = false;         // d_stats3 holds this shard's statistics (no host copy yet)
+    bool stats_on_side = false;           // ... computed on the side stream: consumers wait for ev_stats
     double *d_stats3 = nullptr;
     bool use_comm = false;                // merge the slab with the context's NCCL communicator, in-stream
     int world = 1;                        // ranks the global sample range is sharded over
@@ -170,6 +171,7 @@ struct vx_ctx {
     cudaEvent_t side_done = nullptr;      // everything queued on the side stream so far has finished
     cudaEvent_t ev_sorted = nullptr;      // regime sort of the fold's samples done (side stream)
     cudaEvent_t ev_wins = nullptr;        // window table uploaded and slab cleared (main stream)
+    cudaEvent_t ev_stats = nullptr;       // parameter statistics of the shard reduced (side stream)
     std::string err;
     int64_t launches = 0;
     Job *job = nullptr;
@@ -188,8 +190,8 @@ struct vx_ctx {
     int sm_count = 148;
     // pinned host staging for the copy-backs (a D2H copy into pageable memory blocks the host
     // until it is done, which would serialise the batched grid driver)
-    void *hpin[2] = {nullptr, nullptr};
-    size_t hpin_cap[2] = {0, 0};
+    void *hpin[3] = {nullptr, nullptr, nullptr};
+    size_t hpin_cap[3] = {0, 0, 0};
     std::vector<vx_ctx *> subs;           // vx_run_grid: one sub-context (streams + workspace + job) per box in flight
     // multi-GPU: one NCCL communicator per context (vx_comm_init), used by vx_run_bounds_comm
     void *comm = nullptr;
@@ -240,7 +242,7 @@ int pool_get(vx_ctx *ctx, Slot slot, size_t bytes, void **out)
     return VX_OK;
 }
 
-enum HSlot { HSLOT_SEL = 0, HSLOT_FIN = 1 };
+enum HSlot { HSLOT_SEL = 0, HSLOT_FIN = 1, HSLOT_PLAN = 2 };
 
 int hpin_get(vx_ctx *ctx, HSlot slot, size_t bytes, void **out)
 {
@@ -260,7 +262,7 @@ void pool_release(vx_ctx *ctx)
     cudaSetDevice(ctx->device);
     for (vx_ctx *sub : ctx->subs) vx_destroy(sub);
     ctx->subs.clear();
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
         if (ctx->hpin[i]) cudaFreeHost(ctx->hpin[i]);
         ctx->hpin[i] = nullptr; ctx->hpin_cap[i] = 0;
     }
@@ -506,18 +508,22 @@ int plan_windows(vx_ctx *ctx, bool from_pilot)
     const int64_t words = ACC_HDR + 3 * R + (j->bins64 ? (int64_t)off : (int64_t)((off + 1) / 2));
     { void *p_ = nullptr; int rc_ = pool_get(ctx, SLOT_ACC, sizeof(unsigned long long) * words, &p_); if (rc_) return rc_; j->d_acc = (unsigned long long *)p_; }
     j->acc_words = words;
-    std::vector<Win> hw(R * 2);
-    for (int64_t i = 0; i < R * 2; ++i) hw[i] = j->plan[i].w;
+    // window table and target kinds: built in pinned memory and uploaded with ONE copy (they sit
+    // between the pilot and the fold, where every host microsecond is an idle GPU)
+    const size_t wins_bytes = sizeof(Win) * R * 2, tgt_bytes = sizeof(int) * R * 4;
+    void *hp_ = nullptr;
     { void *p_ = nullptr; int rc_;
-      rc_ = pool_get(ctx, SLOT_WINS, sizeof(Win) * R * 2, &p_); if (rc_) return rc_; j->d_wins = (Win *)p_;
-      rc_ = pool_get(ctx, SLOT_TGT, sizeof(int) * R * 4, &p_); if (rc_) return rc_; j->d_tgt = (int *)p_;
-      rc_ = pool_get(ctx, SLOT_RES, sizeof(long long) * R * 4, &p_); if (rc_) return rc_; j->d_res = (long long *)p_; }
-    std::vector<int> hk(R * 4);
-    for (int64_t i = 0; i < R * 2; ++i)
-        for (int k = 0; k < 2; ++k) hk[i * 2 + k] = j->plan[i].tgt[k];
-    // pageable sources: the async copies return once the data is staged, the vectors may go
-    CK(cudaMemcpyAsync(j->d_wins, hw.data(), sizeof(Win) * R * 2, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(j->d_tgt, hk.data(), sizeof(int) * R * 4, cudaMemcpyHostToDevice, ctx->stream));
+      rc_ = pool_get(ctx, SLOT_WINS, wins_bytes + tgt_bytes, &p_); if (rc_) return rc_;
+      j->d_wins = (Win *)p_; j->d_tgt = (int *)((char *)p_ + wins_bytes);
+      rc_ = pool_get(ctx, SLOT_RES, sizeof(long long) * R * 4, &p_); if (rc_) return rc_; j->d_res = (long long *)p_;
+      rc_ = hpin_get(ctx, HSLOT_PLAN, wins_bytes + tgt_bytes, &hp_); if (rc_) return rc_; }
+    Win *hw = (Win *)hp_;
+    int *hk = (int *)((char *)hp_ + wins_bytes);
+    for (int64_t i = 0; i < R * 2; ++i) {
+        hw[i] = j->plan[i].w;
+        hk[i * 2] = j->plan[i].tgt[0]; hk[i * 2 + 1] = j->plan[i].tgt[1];
+    }
+    CK(cudaMemcpyAsync(j->d_wins, hp_, wins_bytes + tgt_bytes, cudaMemcpyHostToDevice, ctx->stream));
     return VX_OK;
 }
 
@@ -784,6 +790,7 @@ static int create_ctx(vx_ctx **out, int device, bool side_high_priority)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->side_done, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sorted, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_wins, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_stats, cudaEventDisableTiming);
     if (e == cudaSuccess) {
         int sm = 0;
         cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
@@ -810,6 +817,7 @@ void vx_destroy(vx_ctx *ctx)
     if (ctx->side_done) cudaEventDestroy(ctx->side_done);
     if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
     if (ctx->ev_wins) cudaEventDestroy(ctx->ev_wins);
+    if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
     delete ctx;
 }
 
@@ -1141,6 +1149,7 @@ static int accumulate_impl(vx_ctx *ctx, bool sync_end)
         // of p_soft_no ride in header words 2..5 of the slab the ranks all-reduce anyway
         j->stats_in_slab = true;
         if (j->stats_on_device) {
+            if (j->stats_on_side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats, 0));
             vx_stats_to_header_kernel<<<1, 32, 0, ctx->stream>>>(j->d_stats3, (long long)j->shard_count, STATS_FIX, j->d_acc);
             CKL();
         } else {
@@ -1266,6 +1275,7 @@ static int finalize_launch(vx_ctx *ctx)
         CK(cudaMemcpyAsync(hp, j->d_res, sizeof(long long) * R * 4, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(hp + R * 4, j->d_acc, sizeof(long long) * (ACC_HDR + R), cudaMemcpyDeviceToHost, ctx->stream));
     } else if (!j->stats_set && !j->lstats_set && j->stats_on_device) {
+        if (j->stats_on_side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stats, 0));
         CK(cudaMemcpyAsync(hp + R * 5 + ACC_HDR, j->d_stats3, sizeof(double) * 3, cudaMemcpyDeviceToHost, ctx->stream));
         j->stats_fetch_pending = true;
     }
@@ -1404,9 +1414,12 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
         if (acceptance_probability(j->cfg.bounds) >= 0.25 && j->shard_count > 0) {
             rc = need_device(ctx);
             if (rc) return rc;
-            rc = launch_param_stats(ctx, j);
+            // (on the side stream: nothing on the way to the windows waits for them)
+            rc = launch_param_stats(ctx, j, ctx->side);
             if (rc) return rc;
+            CK(cudaEventRecord(ctx->ev_stats, ctx->side));
             j->stats_on_device = true;
+            j->stats_on_side = true;
         } else {
             double st[4];
             rc = vx_job_param_stats(ctx, st);
