@@ -464,6 +464,7 @@ def main():
                "h2d_bytes_per_step": 12 * 8 + 64,                     # the bounds + scalars of vx_config
                "d2h_bytes_per_step": 3 * (3 * T_DAYS + W) * 8 + 64,   # mean/lower/upper of 4 series
                "ms_per_step": 1e3 * float(tt.item()) / len(e2e_s),
+               "ms_median_rank0": 1e3 * statistics.median(e2e_s), "ms_max_rank0": 1e3 * max(e2e_s),
                "api": "run_model(...) of covid19-vaccination-model_b200 (ctypes -> C ABI)"}
 
     # ---------------- north_star check (3): ONE fixed global job, whatever N is.  Its digest must be

@@ -172,6 +172,7 @@ struct vx_ctx {
     cudaEvent_t ev_sorted = nullptr;      // regime sort of the fold's samples done (side stream)
     cudaEvent_t ev_wins = nullptr;        // window table uploaded and slab cleared (main stream)
     cudaEvent_t ev_stats = nullptr;       // parameter statistics of the shard reduced (side stream)
+    cudaEvent_t jev[6] = {nullptr};       // the timing events a job uses (created once, not per job)
     std::string err;
     int64_t launches = 0;
     Job *job = nullptr;
@@ -289,13 +290,7 @@ void free_job(vx_ctx *ctx)
     Job *j = ctx->job;
     if (!j) return;
     cudaSetDevice(ctx->device);
-    if (j->ev0) cudaEventDestroy(j->ev0);
-    if (j->ev1) cudaEventDestroy(j->ev1);
-    if (j->evA) cudaEventDestroy(j->evA);
-    if (j->evB) cudaEventDestroy(j->evB);
-    if (j->evM0) cudaEventDestroy(j->evM0);
-    if (j->evM1) cudaEventDestroy(j->evM1);
-    delete j;
+    delete j;                             // (its events belong to the context)
     ctx->job = nullptr;
 }
 
@@ -818,6 +813,7 @@ void vx_destroy(vx_ctx *ctx)
     if (ctx->ev_sorted) cudaEventDestroy(ctx->ev_sorted);
     if (ctx->ev_wins) cudaEventDestroy(ctx->ev_wins);
     if (ctx->ev_stats) cudaEventDestroy(ctx->ev_stats);
+    for (int i = 0; i < 6; ++i) if (ctx->jev[i]) cudaEventDestroy(ctx->jev[i]);
     delete ctx;
 }
 
@@ -921,12 +917,10 @@ static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_fir
     }
     const int64_t recv_max = (int64_t)j->W * ((int64_t)std::floor(nvmax_hi * (double)cfg->N) + 1);
     j->vmax[0] = cfg->N; j->vmax[1] = 2 * cfg->N; j->vmax[2] = recv_max; j->vmax[3] = recv_max;
-    CK(cudaEventCreate(&j->ev0));
-    CK(cudaEventCreate(&j->ev1));
-    CK(cudaEventCreate(&j->evA));
-    CK(cudaEventCreate(&j->evB));
-    CK(cudaEventCreate(&j->evM0));
-    CK(cudaEventCreate(&j->evM1));
+    for (int i = 0; i < 6; ++i)
+        if (!ctx->jev[i]) CK(cudaEventCreate(&ctx->jev[i]));
+    j->ev0 = ctx->jev[0]; j->ev1 = ctx->jev[1]; j->evA = ctx->jev[2]; j->evB = ctx->jev[3];
+    j->evM0 = ctx->jev[4]; j->evM1 = ctx->jev[5];
     CK(cudaEventRecord(j->ev0, ctx->stream));
     return VX_OK;
 }
