@@ -124,7 +124,7 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * "use_pilot" (0: start from the coarse full-range windows), "sort_samples" (0: fold the
  * shard in id order instead of pressure-bucket order; same integers either way), "chunk_samples"
  * (granularity of the max_running_time check, default 2^20), "exact_poisson" (1: validation
- * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; ~11x slower),
+ * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; 11-18x slower),
  * "side_samples" (samples stepped on a side stream while the pilot runs and folded from their
  * matrix; default 0 = none -- measured neutral on B200; same integers either way).            */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
