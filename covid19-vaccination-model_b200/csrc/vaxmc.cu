@@ -165,6 +165,8 @@ struct vx_ctx {
     void *pool[SLOT_COUNT] = {nullptr};
     size_t pool_cap[SLOT_COUNT] = {0};
     bool trace = false;
+    bool hostprof = false;                // VX_HOSTPROF=1: host timeline of a job on stderr (no extra synchronisation)
+    std::vector<std::pair<const char *, double>> marks;
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t side = nullptr;          // regime sort runs here, under the latency-bound pilot
@@ -272,6 +274,26 @@ void pool_release(vx_ctx *ctx)
         ctx->pool[i] = nullptr;
         ctx->pool_cap[i] = 0;
     }
+}
+
+inline void mark(vx_ctx *c, const char *what)
+{
+    if (c->hostprof)
+        c->marks.emplace_back(what, std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count());
+}
+
+void marks_flush(vx_ctx *c)
+{
+    if (!c->hostprof || c->marks.empty()) return;
+    std::string line = "[vx host us]";
+    char buf[96];
+    for (size_t i = 1; i < c->marks.size(); ++i) {
+        snprintf(buf, sizeof buf, " %s %.1f |", c->marks[i].first, c->marks[i].second - c->marks[i - 1].second);
+        line += buf;
+    }
+    snprintf(buf, sizeof buf, " total %.1f", c->marks.back().second - c->marks.front().second);
+    fprintf(stderr, "%s%s\n", line.c_str(), buf);
+    c->marks.clear();
 }
 
 struct Phase {   // VX_TRACE=1: host wall time of each phase (after a stream sync) on stderr
@@ -773,6 +795,7 @@ static int create_ctx(vx_ctx **out, int device, bool side_high_priority)
     vx_ctx *c = new vx_ctx();
     c->device = device;
     c->trace = getenv("VX_TRACE") != nullptr;
+    c->hostprof = getenv("VX_HOSTPROF") != nullptr;
     cudaError_t e = cudaSetDevice(device);
     int lo_pri = 0, hi_pri = 0;
     if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
@@ -987,13 +1010,17 @@ static int pilot_launch(vx_ctx *ctx, bool on_side)
     if (j->cfg.mode == VX_MODE_EXPECTED) return run_expected(ctx);
 
     const int64_t n = j->cfg.n_samples, R = j->R;
-    alloc_results(j);
-    // certain bounds of every order statistic
-    j->targets.assign(R * 4, Target());
-    for (int64_t r = 0; r < R; ++r)
-        for (int k = 0; k < 4; ++k) { j->targets[r * 4 + k].lo = 0; j->targets[r * 4 + k].hi = j->vmax[series_of_row(j, r)]; }
+    // host-side preparation (result vectors, the certain bounds of every order statistic); done
+    // AFTER the launches below are queued, while the GPU already runs the pilot
+    auto host_prep = [&]() {
+        alloc_results(j);
+        j->targets.assign(R * 4, Target());
+        for (int64_t r = 0; r < R; ++r)
+            for (int k = 0; k < 4; ++k) { j->targets[r * 4 + k].lo = 0; j->targets[r * 4 + k].hi = j->vmax[series_of_row(j, r)]; }
+    };
 
     if (!j->direct && !ctx->use_pilot) {
+        host_prep();
         j->n_pilot = 0;
         j->pilot_stage = 3;      // nothing in flight: plan from the certain bounds
         return VX_OK;
@@ -1071,6 +1098,7 @@ static int pilot_launch(vx_ctx *ctx, bool on_side)
         }
     }
     if (on_side) CK(cudaEventRecord(ctx->side_done, ctx->side));
+    host_prep();
     j->pilot_stage = 2;
     return VX_OK;
 }
@@ -1109,8 +1137,12 @@ int vx_job_pilot(vx_ctx *ctx)
     Phase ph_(ctx, "pilot (total)");
     int rc = pilot_launch(ctx, false);
     if (rc) return rc;
+    mark(ctx, "pilot queued");
     CK(cudaStreamSynchronize(ctx->stream));
-    return pilot_complete(ctx);
+    mark(ctx, "pilot waited");
+    rc = pilot_complete(ctx);
+    mark(ctx, "planned");
+    return rc;
 }
 
 int vx_job_acc(vx_ctx *ctx, void **device_ptr, int64_t *n_words)
@@ -1304,6 +1336,7 @@ static int finalize_complete(vx_ctx *ctx, vx_result *res)
             if (j->merge_timed && cudaEventElapsedTime(&fms, j->evM0, j->evM1) == cudaSuccess) j->merge_ms += fms;
             j->fold_timing_pending = j->merge_timed = false;
         }
+        mark(ctx, "fc events");
         const int64_t n = (int64_t)hdr[0];
         if (n < 1) return fail(ctx, VX_ERR_STATE, "no samples were folded");
         if (j->stats_in_slab) {
@@ -1351,6 +1384,7 @@ static int finalize_complete(vx_ctx *ctx, vx_result *res)
                 if (t.lo == t.hi) { t.resolved = true; t.value = t.lo; }
             }
         }
+        mark(ctx, "fc targets");
         for (const Target &t : j->targets) all = all && t.resolved;
         if (!all) {
             rc = plan_windows(ctx, false);
@@ -1361,6 +1395,7 @@ static int finalize_complete(vx_ctx *ctx, vx_result *res)
         for (int64_t i = 0; i < R * 4; ++i) ord[i] = j->targets[i].value;
         fill_from_counts(j, ord, sums, n);
         j->finished = true;
+        mark(ctx, "fc fill");
     }
     float ms = 0.f;
     cudaEventElapsedTime(&ms, j->ev0, j->ev1);
@@ -1383,6 +1418,7 @@ int vx_job_finalize(vx_ctx *ctx, vx_result *res)
     int rc = finalize_launch(ctx);
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
+    mark(ctx, "fold waited");
     return finalize_complete(ctx, res);
 }
 
@@ -1398,6 +1434,7 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
 {
     Job *j = ctx->job;
     int rc;
+    bool stats_async = false;
     if (!j->explicit_params) {
         // Rejection statistics of the parameter draw.  When most of the (p_pro, p_anti) box is
         // acceptable the 10*n_rep abort cannot trigger and nothing downstream waits for the
@@ -1406,14 +1443,7 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
         // mostly or wholly infeasible) they are read first, as the reference does, so that a job that
         // is going to abort does not run its pilot with millions of rejection attempts per sample.
         if (acceptance_probability(j->cfg.bounds) >= 0.25 && j->shard_count > 0) {
-            rc = need_device(ctx);
-            if (rc) return rc;
-            // (on the side stream: nothing on the way to the windows waits for them)
-            rc = launch_param_stats(ctx, j, ctx->side);
-            if (rc) return rc;
-            CK(cudaEventRecord(ctx->ev_stats, ctx->side));
-            j->stats_on_device = true;
-            j->stats_on_side = true;
+            stats_async = true;           // queued behind the pilot below
         } else {
             double st[4];
             rc = vx_job_param_stats(ctx, st);
@@ -1433,8 +1463,26 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
             }
         }
     }
-    rc = vx_job_pilot(ctx);
-    if (rc) return rc;
+    {
+        Phase ph_(ctx, "pilot (total)");
+        rc = pilot_launch(ctx, false);
+        if (rc) return rc;
+        if (stats_async) {
+            // on the side stream and behind the pilot in host order: nothing on the way to the
+            // windows waits for these kernels
+            rc = launch_param_stats(ctx, j, ctx->side);
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->ev_stats, ctx->side));
+            j->stats_on_device = true;
+            j->stats_on_side = true;
+        }
+        mark(ctx, "pilot queued");
+        CK(cudaStreamSynchronize(ctx->stream));
+        mark(ctx, "pilot waited");
+        rc = pilot_complete(ctx);
+        mark(ctx, "planned");
+        if (rc) return rc;
+    }
     if (counts_out) {
         if (!j->direct || !j->d_dump) return fail(ctx, VX_ERR_ARG, "counts_out needs a direct job (n_samples <= direct_max)");
         CK(cudaMemcpyAsync(counts_out, j->d_dump, sizeof(int32_t) * j->R * j->cfg.n_samples, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1443,7 +1491,9 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
     for (int it = 0; it < 64; ++it) {
         rc = accumulate_impl(ctx, false);
         if (rc) return rc;
+        mark(ctx, "fold queued");
         rc = vx_job_finalize(ctx, res);
+        mark(ctx, "finalized");
         if (rc != VX_REFINE) return rc;
     }
     return fail(ctx, VX_ERR_STATE, "window refinement did not converge");
@@ -1452,11 +1502,15 @@ static int run_job(vx_ctx *ctx, vx_result *res, int32_t *counts_out)
 int vx_run_bounds(vx_ctx *ctx, const vx_config *cfg, vx_result *res)
 {
     if (!ctx || !res) return VX_ERR_ARG;
+    mark(ctx, "enter");
     int rc = job_begin_common(ctx, cfg, 0, cfg ? cfg->n_samples : 0, nullptr);
+    mark(ctx, "begin");
     if (rc == VX_OK) rc = run_job(ctx, res, nullptr);
     const std::string keep = ctx->err;
     free_job(ctx);
     ctx->err = keep;
+    mark(ctx, "free");
+    marks_flush(ctx);
     return rc;
 }
 
