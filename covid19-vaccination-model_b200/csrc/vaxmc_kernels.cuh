@@ -586,6 +586,10 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
     };
     PairRng nx;
     if (PIPE) nx = pair_ahead(0u);
+    // DUMP: this sample's column in the rows of day 0 (n_vacc) and week 0 (doses)
+    int32_t *dump_day = MODE == SIM_DUMP ? a.dump + col : nullptr;
+    int32_t *dump_week = MODE == SIM_DUMP ? a.dump + (int64_t)a.T * a.dump_stride + col : nullptr;
+    const int64_t dump_stock_off = ((int64_t)a.T + 2 * a.W) * a.dump_stride, dump_recv_off = (int64_t)a.W * a.dump_stride;
     for (int d0 = 0; d0 < T; d0 += WIN_DAYS) {
         int *tp = tile + lane;                              // this sample's column of the tile
         const int nd = min(WIN_DAYS, T - d0);               // days in this tile
@@ -628,15 +632,18 @@ __global__ void __launch_bounds__(SIM_THREADS, EXACT ? 4 : (PIPE ? 2 : VX_SIM_MI
                     tile[(28 + wk) * TILE_LD + lane] = dv + q_oldest(d0 / 7 + wk);
                     tile[(30 + wk) * TILE_LD + lane] = n_vacc + stock;
                 }
-            } else if (live) {
-                const int64_t ld = a.dump_stride;
-                a.dump[(int64_t)day * ld + col] = n_vacc;
-                a.dump[((int64_t)T + 2 * W + day) * ld + col] = stock;
-                if (week0) {
-                    const int k = day / 7;
-                    a.dump[((int64_t)T + k) * ld + col] = dv + q_oldest(k);
-                    a.dump[((int64_t)T + W + k) * ld + col] = n_vacc + stock;
+            } else {
+                // row pointers advance by one row a day / a week (no 64-bit index arithmetic per store)
+                if (live) {
+                    dump_day[0] = n_vacc;
+                    dump_day[dump_stock_off] = stock;
+                    if (week0) {
+                        dump_week[0] = dv + q_oldest(d0 / 7 + wk);
+                        dump_week[dump_recv_off] = n_vacc + stock;
+                    }
                 }
+                dump_day += a.dump_stride;
+                if (week0) dump_week += a.dump_stride;
             }
             return dv;
         };
