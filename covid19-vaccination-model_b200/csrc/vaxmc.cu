@@ -926,7 +926,7 @@ static int job_begin_common(vx_ctx *ctx, const vx_config *cfg, int64_t shard_fir
     j->R = 2 * (int64_t)j->T + 2 * (int64_t)j->W;
     j->explicit_params = h_params != nullptr;
     j->bins64 = cfg->n_samples >= ((int64_t)1 << 32) ? 1 : 0;
-    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 65536;   // crossover of direct vs pilot+fold on B200 (USA shape)
+    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : VX_DIRECT_MAX_DEFAULT;   // crossover of direct vs pilot+fold on B200 (USA shape)
     j->direct = (cfg->mode == VX_MODE_EXPECTED) || cfg->n_samples <= dmax;
     j->t_begin = std::chrono::steady_clock::now();
     double nvmax_hi = std::max(cfg->bounds[10], cfg->bounds[11]);
@@ -1700,7 +1700,7 @@ int vx_run_bounds_comm(vx_ctx *ctx, const vx_config *cfg, vx_result *res)
 {
     if (!ctx || !res || !cfg) return VX_ERR_ARG;
     if (!ctx->comm || ctx->comm_world == 1) return vx_run_bounds(ctx, cfg, res);
-    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : 65536;
+    const int64_t dmax = cfg->direct_max > 0 ? cfg->direct_max : VX_DIRECT_MAX_DEFAULT;
     const bool direct = cfg->mode == VX_MODE_EXPECTED || cfg->n_samples <= dmax;
     int64_t first = 0, count = cfg->n_samples;
     if (!direct) vx_host_shard_range(cfg->n_samples, ctx->comm_rank, ctx->comm_world, &first, &count);

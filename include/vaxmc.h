@@ -66,6 +66,10 @@ enum { VX_MODE_STOCHASTIC = 0, /* model.py as written                           
 
 typedef struct vx_ctx vx_ctx;
 
+/* Where materialise + select and pilot + fold cost the same on B200 (USA shape, measured:
+ * 1.7 ms; a direct job is linear in n, 0.84 ms at 65536 samples). */
+#define VX_DIRECT_MAX_DEFAULT 163840
+
 typedef struct vx_config {
     double bounds[12];       /* pro lo,hi; anti lo,hi; pressure lo,hi; tau lo,hi; nv_0 lo,hi;
                                 nv_max lo,hi  (model.py:231-239 argument order), fractions  */
@@ -75,8 +79,8 @@ typedef struct vx_config {
     int64_t n_samples;       /* n_rep: GLOBAL number of Monte Carlo samples                  */
     uint64_t seed;           /* Philox4x32-10 key                                            */
     double q_lo, q_hi;       /* quantile fractions (1-CI)/2 and (1+CI)/2  (model.py:220)     */
-    int64_t direct_max;      /* n_samples <= this: materialise + exact radix select;
-                                above: pilot + streaming fold.  0 = library default          */
+    int64_t direct_max;      /* n_samples <= this: materialise + exact select; above: pilot +
+                                streaming fold.  0 = VX_DIRECT_MAX_DEFAULT                   */
     int64_t pilot_samples;   /* size of the pilot used to place the windows. 0 = default     */
     double max_running_time; /* seconds, <= 0: none (model.py:187-189).  Checked between chunks of
                                 "chunk_samples" of the streaming fold (the first chunk always runs,

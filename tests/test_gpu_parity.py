@@ -667,7 +667,7 @@ def test_run_model_grid_equals_sequential_run_model(vax):
     args.insert(4, ([70, 90], [50, 60], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10]))      # infeasible box
     args.insert(8, ([60, 99], [38, 99], [0, 0.1], [3, 4], [0.2, 0.24], [10, 10]))      # aborts on the rejection count
     seeds = [100 + i for i in range(len(args))]
-    for n_rep, wave in ((150_000, 3), (150_000, 0), (2_000, 5)):                         # streamed jobs, direct jobs
+    for n_rep, wave in ((200_000, 3), (200_000, 0), (2_000, 5)):                         # streamed jobs, direct jobs
         grid = vax.run_model_grid(args, 99, n_rep, 50000, USA_DATES, seeds=seeds, wave=wave)
         assert len(grid) == len(args)
         n_none = 0
