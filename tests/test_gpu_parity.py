@@ -523,19 +523,10 @@ def test_streamed_refinement_paths(vax, ctx):
     assert np.array_equal(d0.lower[2], d0.upper[2])       # deliveries are deterministic here
 
 
-def test_sharding_is_bit_exact(vax, ctx):
-    """1 vs 2 vs 3 vs 8 shards of the same global sample range, merged by integer addition
-    (what the NCCL all-reduce does across GPUs): identical bytes out."""
-    import torch
-
-    nat = vax._native
-    from importlib import import_module
-    dist = import_module("covid19-vaccination-model_b200.distributed")
-    bounds = usa_bounds_frac()
-    n = 40000
-    cfg = _cfg(vax, bounds, n, seed=2025, direct_max=1, pilot_samples=4096)
+def _sharded_equals_single(vax, ctx, nat, dist, torch, bounds, n, pilot, worlds):
+    cfg = _cfg(vax, bounds, n, seed=2025, direct_max=1, pilot_samples=pilot)
     single = ctx.run_bounds(cfg)
-    for world, stats_in_slab in ((2, False), (3, True), (8, True)):
+    for world, stats_in_slab in worlds:
         ctxs = [nat.Context(0) for _ in range(world)]
         engines = [dist.ContextEngine(c) for c in ctxs]
         for r, e in enumerate(engines):
@@ -568,6 +559,25 @@ def test_sharding_is_bit_exact(vax, ctx):
             e.end()
         for c in ctxs:
             c.close()
+
+
+def test_sharding_is_bit_exact(vax, ctx):
+    """1 vs 2 vs 3 vs 8 shards of the same global sample range, merged by integer addition
+    (what the NCCL all-reduce does across GPUs): identical bytes out."""
+    import torch
+
+    nat = vax._native
+    from importlib import import_module
+    dist = import_module("covid19-vaccination-model_b200.distributed")
+    bounds = usa_bounds_frac()
+    # (n, pilot, worlds): the second and third shape put shard boundaries INSIDE the pilot matrix, whose
+    # share of a shard is folded from the matrix (full 8192-column chunks with 16-byte loads, partial
+    # chunks, and an odd leading dimension that takes the scalar path)
+    for n, pilot, worlds in ((40000, 4096, ((2, False), (3, True), (8, True))),
+                             (40000, 24576, ((2, True), (3, True))),
+                             (40001, 20001, ((3, True),))):
+        _sharded_equals_single(vax, ctx, nat, dist, torch, bounds, n, pilot, worlds)
+    n = 40000
     # infeasible bounds discovered through the slab header: every rank reports `aborted`
     bad = _cfg(vax, np.array([0.7, 0.9, 0.5, 0.6, 0, 0.1, 3, 4, 0.002, 0.0024, 0.1, 0.1]), n, seed=3,
                direct_max=1, pilot_samples=4096)

@@ -36,6 +36,8 @@ def test_struct_layout_matches_header(vax):
     assert lib.vx_abi_version() == nat.ABI_VERSION
     hdr = open(os.path.join(ROOT, "include", "vaxmc.h")).read()
     assert int(re.search(r"#define VX_ABI_VERSION (\d+)", hdr).group(1)) == nat.ABI_VERSION
+    # the direct/streamed crossover is decided in the library and mirrored by the Python driver
+    assert int(re.search(r"#define VX_DIRECT_MAX_DEFAULT (\d+)", hdr).group(1)) == nat.DIRECT_MAX_DEFAULT
     assert lib.vx_sizeof(0) == ctypes.sizeof(nat.vx_config)
     assert lib.vx_sizeof(1) == ctypes.sizeof(nat.vx_result)
     assert lib.vx_sizeof(2) == ctypes.sizeof(nat.vx_nccl_id) == 128
