@@ -22,8 +22,9 @@ The first three orders are the known expansion of the continuous inverse of the 
      mode: profiles/r02_sampler_bias_1e9.jsonl).  The refit lowers that bias ~5x, but only by
      inflating the far tail at lam ~ 2 (pmf errors of +20 % at k = 10 to +130 % at k = 12, chi-square
      non-centrality 4e-7 -> 2e-5 per draw), which a goodness-of-fit test at one lam sees with 1e6
-     draws.  The next order of the expansion (a w^5 term, ~5 instructions per day) would be the
-     clean fix.
+     draws.  Adding the lam^-5/2 and lam^-3 orders to the fit (tried) lowers the sup-CDF error to
+     5e-5 but only halves the mean bias: its pattern in lam (+1.1e-4 at 2.5, -1e-4 at 6) is a
+     lattice effect of the floor, not a missing power of lam^-1/2.
 
 Run:  python oracle/fit_poisson_cf.py
 """
