@@ -518,7 +518,7 @@ def main():
     # ---------------- BASELINE configs[4] as a secondary block: 1024 boxes x 1e6 samples, CI=99
     grid = None
     if args.grid_boxes > 0 and args.workload == "usa":
-        grid = time_grid(vax, ctx, rank, world, local_rank, dist, args.grid_boxes, 1_000_000, 99.0, args.grid_wave, 1, 2)
+        grid = time_grid(vax, ctx, rank, world, local_rank, dist, args.grid_boxes, 1_000_000, 99.0, args.grid_wave, 2, 2)
 
     if rank != 0:
         if dist is not None:

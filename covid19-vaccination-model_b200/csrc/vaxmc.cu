@@ -236,7 +236,9 @@ int pool_get(vx_ctx *ctx, Slot slot, size_t bytes, void **out)
         if (ctx->pool[slot]) CK(cudaFree(ctx->pool[slot]));
         ctx->pool[slot] = nullptr;
         ctx->pool_cap[slot] = 0;
-        const size_t want = bytes + bytes / 8;   // a little headroom: window tables grow per pass
+        // headroom: the slab's size follows the window widths, which vary by ~10 % from job to job
+        // (a re-allocation synchronises the device and stalls a pipelined grid)
+        const size_t want = bytes + (slot == SLOT_ACC ? bytes / 2 : bytes / 8);
         cudaError_t e = cudaMalloc(&ctx->pool[slot], want);
         if (e != cudaSuccess) { cudaGetLastError(); CK(cudaMalloc(&ctx->pool[slot], bytes)); ctx->pool_cap[slot] = bytes; }
         else ctx->pool_cap[slot] = want;
