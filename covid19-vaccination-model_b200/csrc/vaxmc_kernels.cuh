@@ -1087,19 +1087,22 @@ __global__ void __launch_bounds__(SEL_THREADS) vx_select_kernel(
 // Order statistics of int32 rows by histogram refinement (the default for int32; the radix kernel
 // above stays for fp64 rows and as a cross-check).  One CTA per row:
 //   pass 0   row sum, min and max (the only pass that looks at every bit of every value)
-//   level 0  4096 bins over [min, max]
-//   level k  all still-open ranks at once, 4096 / #ranks bins each over their bins --
-//            two levels resolve a range of 2^22+, three any int32 row.
+//   level 0  SELS_BINS bins over [min, max]
+//   level k  all still-open ranks at once, SELS_BINS / #ranks bins each over their bins: every
+//            level divides the open ranges by >= 256, so four levels resolve any int32 row.
 // STAGED: the row fits in shared memory (the pilot matrix: 16384 columns = 64 KB per row): it is
 //         read from HBM/L2 ONCE and the levels run on chip.
 // else:   the row is streamed from global memory once per pass with 16-byte loads (1 + levels
 //         reads, typically 3, ~6 instructions per element and pass; the 8-bit radix select needs
 //         1 + 4 reads at ~25 instructions per element and pass).
 constexpr int SELS_THREADS = 512;
-constexpr int SELS_BINS = 4096;
+// 2048 bins (8 KB) next to a 64 KB pilot row = three CTAs per SM (40 registers): measured 0.116 ms
+// for the 1290 x 16384 pilot select against 0.136 ms with 4096 bins and two CTAs per SM
+constexpr int SELS_BINS = 2048;
+constexpr int SELS_CTAS = 3;
 
 template <bool STAGED>
-__global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_hist_kernel(
+__global__ void __launch_bounds__(SELS_THREADS, SELS_CTAS) vx_select_hist_kernel(
     const int32_t *__restrict__ data, int64_t ld, int64_t n, const int64_t *__restrict__ ranks, int nranks,
     int32_t *__restrict__ out /*[rows][nranks]*/, long long *__restrict__ sums /*[rows]*/)
 {
@@ -1204,7 +1207,7 @@ __global__ void __launch_bounds__(SELS_THREADS, 2) vx_select_hist_kernel(
             }
             s_n = nd;
             int per = SELS_BINS;
-            while (per * nd > SELS_BINS) per >>= 1;            // nd <= 8 -> per >= 512
+            while (per * nd > SELS_BINS) per >>= 1;            // nd <= 8 -> per >= 256
             for (int d = 0; d < nd; ++d) {
                 int sh = 0;
                 while (((s_w[d] + ((1ll << sh) - 1)) >> sh) > per) ++sh;
