@@ -101,7 +101,7 @@ typedef struct vx_result {
     int32_t n_passes;        /* streaming passes over the shard that were needed (>= 0)       */
     double device_ms;        /* device time of the job measured with CUDA events              */
     double fold_ms;          /* of which: streaming-fold stepper launches (all passes)        */
-    double pilot_ms;         /* of which: pilot/direct stepper + radix select                 */
+    double pilot_ms;         /* of which: pilot/direct stepper + exact select                 */
     int64_t fold_launches;   /* number of streaming-fold launches behind fold_ms              */
     double merge_ms;         /* of which: the NCCL all-reduce of the slab (vx_run_bounds_comm) */
     int64_t n_pilot;         /* samples of the replicated pilot (0: direct job)               */
@@ -231,7 +231,7 @@ int64_t vx_host_rows(int32_t T);
 int vx_test_philox(vx_ctx *ctx, const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 int vx_test_poisson(vx_ctx *ctx, double lam, int64_t n, uint64_t seed, int32_t *out_host);
 int vx_test_normal(vx_ctx *ctx, int64_t n, uint64_t seed, float *out_host);
-/* exact multi-rank radix select of each row of host int32 data [rows][n]               */
+/* exact multi-rank select of each row of host int32 data [rows][n] (kernel per "select_global") */
 int vx_test_select(vx_ctx *ctx, const int32_t *data, int64_t rows, int64_t n,
                    const int64_t *ranks, int32_t n_ranks, int32_t *out /*[rows][n_ranks]*/,
                    int64_t *sums /*[rows]*/);
