@@ -130,7 +130,10 @@ int vx_device_count(void);              /* 0 when no CUDA device is usable      
  * (granularity of the max_running_time check, default 2^20), "exact_poisson" (1: validation
  * mode, numpy's regimes on the Philox stream -- inversion below 10, PTRS above; 11-18x slower),
  * "side_samples" (samples stepped on a side stream while the pilot runs and folded from their
- * matrix; default 0 = none -- measured neutral on B200; same integers either way).            */
+ * matrix; default 0 = none -- measured neutral on B200; same integers either way),
+ * "select_global" (0: histogram select, rows staged on chip when they fit; 1: the 8-bit radix
+ * select; 2: the histogram select streamed from global memory whatever the row length -- same
+ * integers), "pipe_pilot" (0: the plain stepper also for launches that cannot fill the GPU).   */
 int vx_set_option(vx_ctx *ctx, const char *name, double value);
 /* The context keeps its device workspace (pilot matrix, accumulators) between jobs;
  * vx_trim returns it to the driver. */
