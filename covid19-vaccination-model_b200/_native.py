@@ -22,7 +22,7 @@ SERIES = (
 VX_OK, VX_REFINE = 0, 1
 VX_ERR_NODEVICE = -5
 MODE_STOCHASTIC, MODE_EXPECTED = 0, 1
-DIRECT_MAX_DEFAULT = 163840  # vx_config.direct_max == 0 (include/vaxmc.h: VX_DIRECT_MAX_DEFAULT)
+DIRECT_MAX_DEFAULT = 196608  # vx_config.direct_max == 0 (include/vaxmc.h: VX_DIRECT_MAX_DEFAULT)
 
 
 class VaxmcError(RuntimeError):

@@ -1116,6 +1116,7 @@ __global__ void __launch_bounds__(SELS_THREADS, SELS_CTAS) vx_select_hist_kernel
     __shared__ int t_shift[SEL_MAXR], t_slot[SEL_MAXR], t_open[SEL_MAXR];
     __shared__ long long s_lo[SEL_MAXR], s_w[SEL_MAXR];             // distinct intervals of this level
     __shared__ int s_shift[SEL_MAXR], s_n;
+    __shared__ int s_small;                                         // row range < 2^31: 32-bit interval tests are exact
     __shared__ long long u_lo[SEL_MAXR], u_w[SEL_MAXR], u_rem[SEL_MAXR];   // next level's intervals (written by the bin owners)
     __shared__ uint32_t slot_base[SEL_MAXR];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1188,6 +1189,7 @@ __global__ void __launch_bounds__(SELS_THREADS, SELS_CTAS) vx_select_hist_kernel
         long long a = 0; int lo = INT_MAX, hi = INT_MIN;
         for (int w = 0; w < SELS_THREADS / 32; ++w) { a += red_sum[w]; lo = min(lo, red_min[w]); hi = max(hi, red_max[w]); }
         if (sums) sums[blockIdx.x] = a;
+        s_small = ((long long)hi - lo) < (1ll << 31);
         for (int k = 0; k < nranks; ++k) {
             t_lo[k] = lo; t_w[k] = (long long)hi - lo + 1; t_rem[k] = ranks[k]; t_open[k] = t_w[k] > 1;
         }
@@ -1223,7 +1225,38 @@ __global__ void __launch_bounds__(SELS_THREADS, SELS_CTAS) vx_select_hist_kernel
         for (int i = tid; i < SELS_BINS; i += SELS_THREADS) hist[i] = 0;
         __syncthreads();
         // ---- histogram of the values inside the open intervals
-        if (nd == 1) {
+        // The common shapes take a lean path: one or two open intervals of a row whose range fits 31
+        // bits, tested in 32-bit wrap-around arithmetic ((uint32)(v - lo) < w is exact then), no warp
+        // collectives -- ~5 instructions per value instead of ~20.  A single interval of at most 64
+        // values (a flat or nearly flat row, where same-bin atomics would serialise) and everything
+        // else go through the general code below.
+        if (nd == 1 && s_small && s_w[0] > 64) {
+            const uint32_t lo = (uint32_t)(int)s_lo[0], w = (uint32_t)s_w[0];
+            const int sh = s_shift[0];
+            auto one = [&](const int v) {
+                const uint32_t d = (uint32_t)v - lo;
+                if (d < w) atomicAdd(&hist[d >> sh], 1u);
+            };
+            for_each4([&](const int4 v, const bool ok, const int cnt = 4) {
+                if (!ok) return;
+                one(v.x);
+                if (cnt == 4) { one(v.y); one(v.z); one(v.w); }
+            });
+        } else if (nd == 2 && s_small) {
+            const uint32_t lo0 = (uint32_t)(int)s_lo[0], w0 = (uint32_t)s_w[0], lo1 = (uint32_t)(int)s_lo[1], w1 = (uint32_t)s_w[1];
+            const int sh0 = s_shift[0], sh1 = s_shift[1];
+            uint32_t *hist1 = hist + per;
+            auto one = [&](const int v) {
+                const uint32_t d0 = (uint32_t)v - lo0, d1 = (uint32_t)v - lo1;
+                if (d0 < w0) atomicAdd(&hist[d0 >> sh0], 1u);
+                else if (d1 < w1) atomicAdd(&hist1[d1 >> sh1], 1u);
+            };
+            for_each4([&](const int4 v, const bool ok, const int cnt = 4) {
+                if (!ok) return;
+                one(v.x);
+                if (cnt == 4) { one(v.y); one(v.z); one(v.w); }
+            });
+        } else if (nd == 1) {
             const long long lo = s_lo[0], w = s_w[0];
             const int sh = s_shift[0];
             auto one = [&](const int v, const bool ok) {

@@ -67,8 +67,8 @@ enum { VX_MODE_STOCHASTIC = 0, /* model.py as written                           
 typedef struct vx_ctx vx_ctx;
 
 /* Where materialise + select and pilot + fold cost the same on B200 (USA shape, measured:
- * 1.7 ms; a direct job is linear in n, 0.84 ms at 65536 samples). */
-#define VX_DIRECT_MAX_DEFAULT 163840
+ * 1.7 ms; a direct job is linear in n, 0.73 ms at 65536 samples). */
+#define VX_DIRECT_MAX_DEFAULT 196608
 
 typedef struct vx_config {
     double bounds[12];       /* pro lo,hi; anti lo,hi; pressure lo,hi; tau lo,hi; nv_0 lo,hi;
