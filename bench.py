@@ -299,7 +299,7 @@ def time_grid(vax, ctx, rank, world, local_rank, dist, n_boxes, samples, ci, wav
             "boxes": n_boxes, "samples_per_box": samples, "days": T_DAYS, "N": N_POP,
             "generator": "bench.grid_boxes(seed=20261019)",
             "sample_weeks_per_s": units * steps / sum(per_step), "ms_per_step": 1e3 * sum(per_step) / steps,
-            "step_ms": [1e3 * x for x in per_step],
+            "step_ms": [1e3 * x for x in per_step], "median_step_ms": 1e3 * statistics.median(per_step),
             "step_spread": (max(per_step) - min(per_step)) / (sum(per_step) / steps) if steps > 1 else 0.0,
             "steps": steps, "warmup": warmup, "grid_wave": wave, "gpu_launches": ctx.launch_count - l0,
             "timing": "host wall clock around the whole grid incl. D2H of every box's bands (max over ranks)"}
@@ -518,7 +518,7 @@ def main():
     # ---------------- BASELINE configs[4] as a secondary block: 1024 boxes x 1e6 samples, CI=99
     grid = None
     if args.grid_boxes > 0 and args.workload == "usa":
-        grid = time_grid(vax, ctx, rank, world, local_rank, dist, args.grid_boxes, 1_000_000, 99.0, args.grid_wave, 2, 2)
+        grid = time_grid(vax, ctx, rank, world, local_rank, dist, args.grid_boxes, 1_000_000, 99.0, args.grid_wave, 2, 3)
 
     if rank != 0:
         if dist is not None:
